@@ -1,0 +1,91 @@
+// Shared host/device utilities of the linetr_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+namespace ltr {
+
+// ---------------------------------------------------------------- error reporting
+extern thread_local std::string g_last_error;
+int set_error(int code, const std::string& msg);
+
+#define LTR_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return ::ltr::set_error(-2, std::string(#expr) + ": " + cudaGetErrorString(_e));  \
+  } while (0)
+
+// ---------------------------------------------------------------- instrumentation
+// Kernel classes for launch counting and per-class CUDA-event timing (ltr_profile_*).
+enum KernelClass : int {
+  KC_SMALL_MLP = 0,
+  KC_LINEAR,
+  KC_CLS_POOL,
+  KC_LAYERNORM,
+  KC_SIG_ATTN,
+  KC_FINAL_NORM,
+  KC_DIST,
+  KC_SEGMEAN,
+  KC_ARGMIN,
+  KC_MUTUAL,
+  KC_TOKEN_FUSED,
+  KC_LINE_FUSED,
+  KC_SIG_FUSED,
+  KC_COUNT
+};
+const char* kernel_class_name(int kc);
+
+extern std::atomic<int64_t> g_launches;
+
+struct Profiler {
+  bool on = false;
+  struct Rec { int kc; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get();
+};
+extern Profiler g_prof;
+
+// RAII bracket around one kernel launch: counts it, and when profiling is armed records
+// CUDA events on the launching stream (so the measurement sees exactly that kernel).
+struct LaunchScope {
+  cudaStream_t s;
+  int idx = -1;
+  LaunchScope(int kc, cudaStream_t stream) : s(stream) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_prof.on) {
+      Profiler::Rec r{kc, g_prof.get(), g_prof.get()};
+      cudaEventRecord(r.a, s);
+      g_prof.recs.push_back(r);
+      idx = (int)g_prof.recs.size() - 1;
+    }
+  }
+  ~LaunchScope() {
+    if (idx >= 0) cudaEventRecord(g_prof.recs[idx].b, s);
+  }
+};
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Lines of image i: [begin, end).  cu == nullptr means a uniform batch of lpi lines/image.
+__device__ __forceinline__ void image_range(const int* __restrict__ cu, int lpi, int i, int& b, int& e) {
+  if (cu) { b = cu[i]; e = cu[i + 1]; } else { b = i * lpi; e = b + lpi; }
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace ltr

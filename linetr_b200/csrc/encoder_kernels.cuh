@@ -1,0 +1,397 @@
+// CUDA-core kernels of the line-descriptor forward that are not GEMMs:
+// narrow positional-encoder layers, folded CLS attention pooling, LayerNorm,
+// line-signature attention, final L2 normalisation.
+#pragma once
+#include "common.cuh"
+
+namespace ltr {
+
+// ------------------------------------------------------------------------------------
+// Narrow head of the positional encoders: IN -> 32 -> 64 -> 128, eval-BatchNorm folded,
+// ReLU after each layer.  Reference: MLP() models/line_transformer.py:9-20 as used by
+// WordPositionalEncoder (:61-73, IN = 3: x, y, score) and LinePositionalEncoder (:46-50,
+// IN = 5: mid x, mid y, response, cos2t, sin2t), after normalize_keylines (:22-38).
+// One warp owns SM_ROWS rows at a time; weights live in shared memory.
+struct SmallMlpWeights {
+  const float* w1;  // [32][IN]
+  const float* b1;  // [32]
+  const float* w2;  // [64][32]
+  const float* b2;
+  const float* w3;  // [128][64]
+  const float* b3;
+};
+
+constexpr int SM_ROWS = 4;
+constexpr int SM_WARPS = 8;
+constexpr int SM_K2 = 32 + 4, SM_K3 = 64 + 4;  // padded leading dims (bank-conflict-free float4)
+
+template <int IN>
+struct SmallMlpSmem {
+  float w1[32 * IN];
+  float b1[32], b2[64], b3[128];
+  __align__(16) float w2[64 * SM_K2];
+  __align__(16) float w3[128 * SM_K3];
+  __align__(16) float h1[SM_WARPS][SM_ROWS][32];
+  __align__(16) float h2[SM_WARPS][SM_ROWS][64];
+};
+
+// TOKEN = true : row = token, inputs pnt[row][2], score[row]
+// TOKEN = false: row = line,  inputs sublines[row][2][2], resp[row], angle[row][2]
+template <bool TOKEN>
+__global__ void __launch_bounds__(SM_WARPS * 32)
+small_mlp_kernel(SmallMlpWeights w, const float* __restrict__ in0, const float* __restrict__ in1,
+                 const float* __restrict__ in2, float* __restrict__ out, int rows, float cx, float cy,
+                 float scale) {
+  constexpr int IN = TOKEN ? 3 : 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto& S = *reinterpret_cast<SmallMlpSmem<IN>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 32 * IN; i += blockDim.x) S.w1[i] = w.w1[i];
+  for (int i = tid; i < 32; i += blockDim.x) S.b1[i] = w.b1[i];
+  for (int i = tid; i < 64; i += blockDim.x) S.b2[i] = w.b2[i];
+  for (int i = tid; i < 128; i += blockDim.x) S.b3[i] = w.b3[i];
+  for (int i = tid; i < 64 * 32; i += blockDim.x) S.w2[(i >> 5) * SM_K2 + (i & 31)] = w.w2[i];
+  for (int i = tid; i < 128 * 64; i += blockDim.x) S.w3[(i >> 6) * SM_K3 + (i & 63)] = w.w3[i];
+  __syncthreads();
+
+  const int groups = (rows + SM_ROWS - 1) / SM_ROWS;
+  for (int g = blockIdx.x * SM_WARPS + warp; g < groups; g += gridDim.x * SM_WARPS) {
+    const int r0 = g * SM_ROWS;
+    // layer 1: lane = output channel
+    float x[SM_ROWS][IN];
+#pragma unroll
+    for (int r = 0; r < SM_ROWS; ++r) {
+      int row = min(r0 + r, rows - 1);
+      if (TOKEN) {
+        x[r][0] = (in0[2 * row] - cx) / scale;
+        x[r][1] = (in0[2 * row + 1] - cy) / scale;
+        x[r][2] = in1[row];
+      } else {
+        // normalise both end points first, then take the mid point (reference order)
+        float ax = (in0[4 * row + 0] - cx) / scale, ay = (in0[4 * row + 1] - cy) / scale;
+        float bx = (in0[4 * row + 2] - cx) / scale, by = (in0[4 * row + 3] - cy) / scale;
+        x[r][0] = (ax + bx) / 2.f;
+        x[r][1] = (ay + by) / 2.f;
+        x[r][2] = in1[row];
+        x[r][3] = in2[2 * row];
+        x[r][4] = in2[2 * row + 1];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SM_ROWS; ++r) {
+      float a = S.b1[lane];
+#pragma unroll
+      for (int i = 0; i < IN; ++i) a = fmaf(S.w1[lane * IN + i], x[r][i], a);
+      S.h1[warp][r][lane] = fmaxf(a, 0.f);
+    }
+    __syncwarp();
+    // layer 2: lane owns channels lane, lane+32
+    {
+      float acc[2][SM_ROWS];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) acc[j][r] = S.b2[lane + 32 * j];
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        float4 h[SM_ROWS];
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) h[r] = *reinterpret_cast<const float4*>(&S.h1[warp][r][k4 * 4]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float4 ww = *reinterpret_cast<const float4*>(&S.w2[(lane + 32 * j) * SM_K2 + k4 * 4]);
+#pragma unroll
+          for (int r = 0; r < SM_ROWS; ++r) {
+            acc[j][r] = fmaf(ww.x, h[r].x, acc[j][r]);
+            acc[j][r] = fmaf(ww.y, h[r].y, acc[j][r]);
+            acc[j][r] = fmaf(ww.z, h[r].z, acc[j][r]);
+            acc[j][r] = fmaf(ww.w, h[r].w, acc[j][r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) S.h2[warp][r][lane + 32 * j] = fmaxf(acc[j][r], 0.f);
+    }
+    __syncwarp();
+    // layer 3: lane owns channels lane + 32 j, j < 4
+    {
+      float acc[4][SM_ROWS];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) acc[j][r] = S.b3[lane + 32 * j];
+#pragma unroll 4
+      for (int k4 = 0; k4 < 16; ++k4) {
+        float4 h[SM_ROWS];
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) h[r] = *reinterpret_cast<const float4*>(&S.h2[warp][r][k4 * 4]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 ww = *reinterpret_cast<const float4*>(&S.w3[(lane + 32 * j) * SM_K3 + k4 * 4]);
+#pragma unroll
+          for (int r = 0; r < SM_ROWS; ++r) {
+            acc[j][r] = fmaf(ww.x, h[r].x, acc[j][r]);
+            acc[j][r] = fmaf(ww.y, h[r].y, acc[j][r]);
+            acc[j][r] = fmaf(ww.z, h[r].z, acc[j][r]);
+            acc[j][r] = fmaf(ww.w, h[r].w, acc[j][r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < SM_ROWS; ++r) {
+        int row = r0 + r;
+        if (row < rows) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) out[(long long)row * 128 + lane + 32 * j] = fmaxf(acc[j][r], 0.f);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Folded CLS-row token attention pooling (models/line_attention.py:13-21,42-75 restricted
+// to query row 0, the only row the reference consumes - models/line_transformer.py:128).
+// The CLS query is a model constant, so q_h . k_h[n] / 8 = x[n] . u_h + const_h with
+// u_h = W_k,h^T q_h / 8; the constant cancels in the softmax.  Output per line and head:
+// z_h = sum_n softmax_n(s_h)[n] * x[n]   (n = 0 is the CLS token itself), which the caller
+// multiplies by W_v,h (sum of probabilities is 1, so the V bias passes through).
+// x: [lines*T, 256] (= desc + word positional encoding); z: [lines, 4*256].
+constexpr int CP_THREADS = 256;
+constexpr int CP_MAXN = 129;  // T <= 128
+
+__global__ void __launch_bounds__(CP_THREADS)
+cls_pool_kernel(const float* __restrict__ x, const float* __restrict__ U /*[4][256]*/,
+                const float* __restrict__ s_cls /*[4]*/, const float* __restrict__ cls /*[256]*/,
+                float* __restrict__ z, int T) {
+  __shared__ float sc[CP_MAXN][4];
+  const int line = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ xl = x + (long long)line * T * 256;
+  // scores: warp per token, lanes over channels (8 per lane)
+  float4 u[4][2];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    u[h][0] = *reinterpret_cast<const float4*>(U + h * 256 + lane * 4);
+    u[h][1] = *reinterpret_cast<const float4*>(U + h * 256 + 128 + lane * 4);
+  }
+  for (int n = warp; n < T; n += CP_THREADS / 32) {
+    float4 a = *reinterpret_cast<const float4*>(xl + n * 256 + lane * 4);
+    float4 b = *reinterpret_cast<const float4*>(xl + n * 256 + 128 + lane * 4);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float d = a.x * u[h][0].x + a.y * u[h][0].y + a.z * u[h][0].z + a.w * u[h][0].w +
+                b.x * u[h][1].x + b.y * u[h][1].y + b.z * u[h][1].z + b.w * u[h][1].w;
+      d = warp_sum(d);
+      if (lane == 0) sc[n + 1][h] = d;
+    }
+  }
+  if (tid < 4) sc[0][tid] = s_cls[tid];
+  __syncthreads();
+  // softmax over n = 0..T per head: warp h handles head h
+  if (warp < 4) {
+    const int h = warp, N = T + 1;
+    float m = -INFINITY;
+    for (int n = lane; n < N; n += 32) m = fmaxf(m, sc[n][h]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int n = lane; n < N; n += 32) {
+      float e = expf(sc[n][h] - m);
+      sc[n][h] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    float inv = 1.f / s;
+    for (int n = lane; n < N; n += 32) sc[n][h] *= inv;
+  }
+  __syncthreads();
+  // pooling: thread = channel
+  const int c = tid;
+  float cv = cls[c];
+  float z0 = sc[0][0] * cv, z1 = sc[0][1] * cv, z2 = sc[0][2] * cv, z3 = sc[0][3] * cv;
+  for (int n = 0; n < T; ++n) {
+    float xv = xl[n * 256 + c];
+    z0 = fmaf(sc[n + 1][0], xv, z0);
+    z1 = fmaf(sc[n + 1][1], xv, z1);
+    z2 = fmaf(sc[n + 1][2], xv, z2);
+    z3 = fmaf(sc[n + 1][3], xv, z3);
+  }
+  float* zl = z + (long long)line * 1024;
+  zl[c] = z0; zl[256 + c] = z1; zl[512 + c] = z2; zl[768 + c] = z3;
+}
+
+// ------------------------------------------------------------------------------------
+// LayerNorm over 256 channels, eps inside the sqrt, biased variance
+// (nn.LayerNorm(d, eps=1e-6), models/line_attention.py:40,83); optional fused add of a
+// second row-major tensor AFTER the normalisation (sentence = klines_pos + enc_out,
+// models/line_transformer.py:128).  One warp per row.
+__global__ void __launch_bounds__(256)
+layernorm256_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ add, int lda,
+                    float* __restrict__ out, int ldo, int rows, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = in + (long long)row * ldi;
+  float4 a = *reinterpret_cast<const float4*>(p + lane * 4);
+  float4 b = *reinterpret_cast<const float4*>(p + 128 + lane * 4);
+  float mean = warp_sum(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w) * (1.f / 256.f);
+  float v[8] = {a.x - mean, a.y - mean, a.z - mean, a.w - mean, b.x - mean, b.y - mean, b.z - mean, b.w - mean};
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
+  float var = warp_sum(ss) * (1.f / 256.f);
+  float inv = 1.f / sqrtf(var + eps);
+  float4 g0 = *reinterpret_cast<const float4*>(gamma + lane * 4), g1 = *reinterpret_cast<const float4*>(gamma + 128 + lane * 4);
+  float4 b0 = *reinterpret_cast<const float4*>(beta + lane * 4), b1 = *reinterpret_cast<const float4*>(beta + 128 + lane * 4);
+  float4 o0 = make_float4(v[0] * inv * g0.x + b0.x, v[1] * inv * g0.y + b0.y, v[2] * inv * g0.z + b0.z, v[3] * inv * g0.w + b0.w);
+  float4 o1 = make_float4(v[4] * inv * g1.x + b1.x, v[5] * inv * g1.y + b1.y, v[6] * inv * g1.z + b1.z, v[7] * inv * g1.w + b1.w);
+  if (add) {
+    const float* q = add + (long long)row * lda;
+    float4 c0 = *reinterpret_cast<const float4*>(q + lane * 4), c1 = *reinterpret_cast<const float4*>(q + 128 + lane * 4);
+    o0.x += c0.x; o0.y += c0.y; o0.z += c0.z; o0.w += c0.w;
+    o1.x += c1.x; o1.y += c1.y; o1.z += c1.z; o1.w += c1.w;
+  }
+  float* o = out + (long long)row * ldo;
+  *reinterpret_cast<float4*>(o + lane * 4) = o0;
+  *reinterpret_cast<float4*>(o + 128 + lane * 4) = o1;
+}
+
+// ------------------------------------------------------------------------------------
+// Line-signature attention, one image and head per CTA column: softmax(q k^T / 8) v over
+// the L_i lines of ONE image, no mask (attention(), models/line_transformer.py:132-136).
+// qkv: [n_lines, 768] = [q | k | v], each head-major (c = h*64 + d; the reference's
+// interleaved c = d*4 + h layout is undone when the weights are packed, and 1/8 is folded
+// into W_q).  One thread per query row, keys/values staged through shared memory in
+// tiles of 64, online softmax in chunks of 16 keys.  out: [n_lines, ldo] head-major.
+constexpr int SA_THREADS = 128, SA_KT = 64, SA_CH = 16;
+
+__global__ void __launch_bounds__(SA_THREADS)
+sig_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int ldo,
+                     const int* __restrict__ cu, int lpi) {
+  __shared__ __align__(16) float Ks[SA_KT][64];
+  __shared__ __align__(16) float Vs[SA_KT][64];
+  int lb, le;
+  image_range(cu, lpi, blockIdx.z, lb, le);
+  const int L = le - lb;
+  const int q0 = blockIdx.x * SA_THREADS;
+  if (q0 >= L) return;
+  const int h = blockIdx.y, tid = threadIdx.x;
+  const int qi = q0 + tid;
+  const bool active = qi < L;
+  float q[64], o[64];
+  {
+    const float* qp = qkv + (long long)(lb + (active ? qi : 0)) * 768 + h * 64;
+#pragma unroll
+    for (int d = 0; d < 64; d += 4) {
+      float4 t = *reinterpret_cast<const float4*>(qp + d);
+      q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 64; ++d) o[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+
+  for (int k0 = 0; k0 < L; k0 += SA_KT) {
+    __syncthreads();
+    // stage K and V tiles: 64 keys x 16 float4 each, coalesced
+    for (int i = tid; i < SA_KT * 16; i += SA_THREADS) {
+      int j = i >> 4, c4 = (i & 15) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + j < L) {
+        const float* base = qkv + (long long)(lb + k0 + j) * 768 + h * 64 + c4;
+        kv = *reinterpret_cast<const float4*>(base + 256);
+        vv = *reinterpret_cast<const float4*>(base + 512);
+      }
+      *reinterpret_cast<float4*>(&Ks[j][c4]) = kv;
+      *reinterpret_cast<float4*>(&Vs[j][c4]) = vv;
+    }
+    __syncthreads();
+    const int kn = min(SA_KT, L - k0);
+    for (int c0 = 0; c0 < kn; c0 += SA_CH) {
+      float s[SA_CH];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < SA_CH; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 64; d += 4) {
+          float4 kk = *reinterpret_cast<const float4*>(&Ks[c0 + j][d]);
+          a = fmaf(q[d], kk.x, a); a = fmaf(q[d + 1], kk.y, a);
+          a = fmaf(q[d + 2], kk.z, a); a = fmaf(q[d + 3], kk.w, a);
+        }
+        s[j] = (c0 + j < kn) ? a : -INFINITY;
+        cmax = fmaxf(cmax, s[j]);
+      }
+      float mn = fmaxf(m, cmax);
+      float scale = expf(m - mn);  // exp(-inf) = 0 on the first chunk
+      l *= scale;
+#pragma unroll
+      for (int d = 0; d < 64; ++d) o[d] *= scale;
+#pragma unroll
+      for (int j = 0; j < SA_CH; ++j) {
+        float pj = expf(s[j] - mn);
+        l += pj;
+#pragma unroll
+        for (int d = 0; d < 64; d += 4) {
+          float4 vv = *reinterpret_cast<const float4*>(&Vs[c0 + j][d]);
+          o[d] = fmaf(pj, vv.x, o[d]); o[d + 1] = fmaf(pj, vv.y, o[d + 1]);
+          o[d + 2] = fmaf(pj, vv.z, o[d + 2]); o[d + 3] = fmaf(pj, vv.w, o[d + 3]);
+        }
+      }
+      m = mn;
+    }
+  }
+  if (active) {
+    float inv = 1.f / l;
+    float* op = out + (long long)(lb + qi) * ldo + h * 64;
+#pragma unroll
+    for (int d = 0; d < 64; d += 4)
+      *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// F.normalize(p=2, dim=channel, eps=1e-12) of the final projection
+// (models/line_transformer.py:245-246) and the write of both output layouts:
+// rows [n_lines, 256] and channel-first per image [256, L_i] (the reference's line_desc).
+__global__ void __launch_bounds__(256)
+final_norm_kernel(const float* __restrict__ y, float* __restrict__ out_rows, float* __restrict__ out_cf,
+                  const int* __restrict__ cu, int lpi) {
+  __shared__ float tile[32][257];
+  int lb, le;
+  image_range(cu, lpi, blockIdx.y, lb, le);
+  const int L = le - lb, l0 = blockIdx.x * 32;
+  if (l0 >= L) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int r = warp; r < 32; r += 8) {
+    int li = l0 + r;
+    if (li < L) {
+      const float* p = y + (long long)(lb + li) * 256;
+      float4 a = *reinterpret_cast<const float4*>(p + lane * 4);
+      float4 b = *reinterpret_cast<const float4*>(p + 128 + lane * 4);
+      float ss = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+      ss = warp_sum(ss);
+      float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+      b.x *= inv; b.y *= inv; b.z *= inv; b.w *= inv;
+      if (out_rows) {
+        float* o = out_rows + (long long)(lb + li) * 256;
+        *reinterpret_cast<float4*>(o + lane * 4) = a;
+        *reinterpret_cast<float4*>(o + 128 + lane * 4) = b;
+      }
+      tile[r][lane * 4 + 0] = a.x; tile[r][lane * 4 + 1] = a.y; tile[r][lane * 4 + 2] = a.z; tile[r][lane * 4 + 3] = a.w;
+      tile[r][128 + lane * 4 + 0] = b.x; tile[r][128 + lane * 4 + 1] = b.y;
+      tile[r][128 + lane * 4 + 2] = b.z; tile[r][128 + lane * 4 + 3] = b.w;
+    }
+  }
+  if (!out_cf) return;
+  __syncthreads();
+  float* base = out_cf + (long long)lb * 256;
+  if (l0 + lane < L) {
+    for (int c = warp; c < 256; c += 8) base[(long long)c * L + l0 + lane] = tile[lane][c];
+  }
+}
+
+}  // namespace ltr

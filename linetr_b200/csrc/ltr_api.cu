@@ -1,0 +1,605 @@
+// C ABI of linetr_b200 (see include/linetr_b200.h): checkpoint folding/packing, workspace
+// carving and the launch sequence of the line-descriptor forward and the matcher.
+#include "../../include/linetr_b200.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "encoder_kernels.cuh"
+#include "linear_f32.cuh"
+#include "match_kernels.cuh"
+
+namespace ltr {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+Profiler g_prof;
+
+int set_error(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+const char* kernel_class_name(int kc) {
+  static const char* names[KC_COUNT] = {"small_mlp", "linear", "cls_pool", "layernorm", "sig_attention",
+                                         "final_norm", "dist", "segmean", "argmin", "mutual",
+                                         "token_fused", "line_fused", "sig_fused"};
+  return (kc >= 0 && kc < KC_COUNT) ? names[kc] : "?";
+}
+
+cudaEvent_t Profiler::get() {
+  if (!pool.empty()) {
+    cudaEvent_t e = pool.back();
+    pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// ------------------------------------------------------------------ packed model
+struct MlpTail {  // the two wide layers of a positional encoder (128->256 relu, 256->256)
+  SmallMlpWeights head;
+  float *w4, *b4, *w5, *b5;
+};
+
+struct SigLayer {
+  float *wqkv, *bqkv;  // [768,256] head-major rows, q rows pre-scaled by 1/8
+  float *wm, *bm;      // [256,256] merge, input columns head-major
+  float *w1, *b1;      // [512,512] BN folded
+  float *w2, *b2;      // [256,512]
+};
+
+}  // namespace ltr
+
+struct LtrModel {
+  int device = 0;
+  LtrConfig cfg{};
+  float* arena = nullptr;
+  size_t arena_floats = 0;
+  ltr::MlpTail wpe{}, lpe{};
+  float *U = nullptr, *s_cls = nullptr, *cls = nullptr;
+  float *wv = nullptr, *bv = nullptr, *wfc = nullptr, *bfc = nullptr, *ln1g = nullptr, *ln1b = nullptr;
+  float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+  std::vector<ltr::SigLayer> sig;
+  float *wf = nullptr, *bf = nullptr;
+  int token_chunk = 32768;  // tokens per pass of the token stage (keeps intermediates in L2)
+};
+
+namespace ltr {
+
+using TensorMap = std::unordered_map<std::string, std::pair<const float*, int64_t>>;
+
+struct HostPack {
+  std::vector<float> buf;
+  size_t add(const std::vector<double>& v) {
+    size_t off = (buf.size() + 63) / 64 * 64;  // 256-byte alignment of every tensor
+    buf.resize(off + v.size());
+    for (size_t i = 0; i < v.size(); ++i) buf[off + i] = (float)v[i];
+    return off;
+  }
+};
+
+static bool fetch(const TensorMap& tm, const std::string& name, int64_t numel, const float** out, std::string& err) {
+  auto it = tm.find(name);
+  if (it == tm.end()) { err = "missing checkpoint tensor '" + name + "'"; return false; }
+  if (it->second.second != numel) {
+    err = "checkpoint tensor '" + name + "' has " + std::to_string(it->second.second) + " elements, expected " +
+          std::to_string(numel);
+    return false;
+  }
+  *out = it->second.first;
+  return true;
+}
+
+// Conv1d(k=1)/Linear [out,in] (+ eval BatchNorm1d at bn_prefix, eps 1e-5) -> folded W, b in fp64.
+static bool fold_layer(const TensorMap& tm, const std::string& conv, const std::string& bn, int out, int in,
+                       std::vector<double>& W, std::vector<double>& b, std::string& err) {
+  const float *w, *bias;
+  if (!fetch(tm, conv + ".weight", (int64_t)out * in, &w, err) || !fetch(tm, conv + ".bias", out, &bias, err)) return false;
+  W.assign((size_t)out * in, 0.0);
+  b.assign(out, 0.0);
+  for (int o = 0; o < out; ++o) {
+    double s = 1.0, shift = 0.0;
+    if (!bn.empty()) {
+      const float *g, *be, *mu, *var;
+      if (!fetch(tm, bn + ".weight", out, &g, err) || !fetch(tm, bn + ".bias", out, &be, err) ||
+          !fetch(tm, bn + ".running_mean", out, &mu, err) || !fetch(tm, bn + ".running_var", out, &var, err))
+        return false;
+      s = (double)g[o] / std::sqrt((double)var[o] + 1e-5);
+      shift = (double)be[o] - (double)mu[o] * s;
+    }
+    for (int i = 0; i < in; ++i) W[(size_t)o * in + i] = (double)w[(size_t)o * in + i] * s;
+    b[o] = (double)bias[o] * s + shift;
+  }
+  return true;
+}
+
+struct MlpOffsets { size_t w[5], b[5]; };
+
+static bool pack_pos_encoder(const TensorMap& tm, const std::string& prefix, int in, HostPack& hp, MlpOffsets& off,
+                             std::string& err) {
+  const int ch[6] = {in, 32, 64, 128, 256, 256};
+  for (int l = 0; l < 5; ++l) {
+    std::string conv = prefix + "." + std::to_string(3 * l);
+    std::string bn = (l < 4) ? prefix + "." + std::to_string(3 * l + 1) : std::string();
+    std::vector<double> W, b;
+    if (!fold_layer(tm, conv, bn, ch[l + 1], ch[l], W, b, err)) return false;
+    off.w[l] = hp.add(W);
+    off.b[l] = hp.add(b);
+  }
+  return true;
+}
+
+static void bind_mlp(MlpTail& m, float* base, const MlpOffsets& o) {
+  m.head.w1 = base + o.w[0]; m.head.b1 = base + o.b[0];
+  m.head.w2 = base + o.w[1]; m.head.b2 = base + o.b[1];
+  m.head.w3 = base + o.w[2]; m.head.b3 = base + o.b[2];
+  m.w4 = base + o.w[3]; m.b4 = base + o.b[3];
+  m.w5 = base + o.w[4]; m.b5 = base + o.b[4];
+}
+
+static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ------------------------------------------------------------------ workspace
+struct EncodeWs {
+  float *h128, *h256, *x;                       // token stage, one chunk
+  float *z, *ctx, *y1, *y2, *l128, *l256, *lpos;  // line stage ([R, *])
+  float *xm, *qkv, *o, *hm, *yf;                // signature stage
+  int chunk_lines;
+  int64_t bytes;
+};
+
+static EncodeWs carve(const LtrModel* m, int n_lines, int T, char* base) {
+  EncodeWs w{};
+  int64_t off = 0;
+  auto take = [&](int64_t floats) {
+    float* p = reinterpret_cast<float*>(base + off);
+    off = align_up(off + floats * 4, 256);
+    return p;
+  };
+  int cl = m->token_chunk / T;
+  if (cl < 1) cl = 1;
+  if (cl > n_lines) cl = n_lines > 0 ? n_lines : 1;
+  w.chunk_lines = cl;
+  const int64_t ct = (int64_t)cl * T, R = n_lines;
+  w.h128 = take(ct * 128);
+  w.h256 = take(ct * 256);
+  w.x = take(ct * 256);
+  w.z = take(R * 1024);  // also the FFN hidden buffer
+  w.ctx = take(R * 256);
+  w.y1 = take(R * 256);
+  w.y2 = take(R * 256);
+  w.l128 = take(R * 128);
+  w.l256 = take(R * 256);
+  w.lpos = take(R * 256);
+  w.xm = take(R * 512);
+  w.qkv = take(R * 768);
+  w.o = take(R * 256);
+  w.hm = take(R * 512);
+  w.yf = take(R * 256);
+  w.bytes = off;
+  return w;
+}
+
+static LinearArgs lin(const float* A, int lda, const float* W, const float* b, float* C, int ldc, int M, int N, int K,
+                      int act, const float* R = nullptr, int ldr = 0) {
+  LinearArgs a{};
+  a.A = A; a.lda = lda; a.W = W; a.bias = b; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc;
+  a.M = M; a.N = N; a.K = K; a.act = act; a.nz = 1;
+  return a;
+}
+
+template <bool TOKEN>
+static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const float* in1, const float* in2, float* out,
+                            int rows, float width, float height, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  constexpr int IN = TOKEN ? 3 : 5;
+  static bool attr_set = false;
+  const int smem = (int)sizeof(SmallMlpSmem<IN>);
+  if (!attr_set) {
+    LTR_CUDA_TRY(cudaFuncSetAttribute(small_mlp_kernel<TOKEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int groups = cdiv(rows, SM_ROWS);
+  int grid = cdiv(groups, SM_WARPS);
+  if (grid > 148 * 3) grid = 148 * 3;
+  const float scale = fmaxf(width, height) * 0.7f;
+  LaunchScope ls(KC_SMALL_MLP, s);
+  small_mlp_kernel<TOKEN><<<grid, SM_WARPS * 32, smem, s>>>(w, in0, in1, in2, out, rows, width / 2.f, height / 2.f, scale);
+  LTR_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int launch_layernorm(const float* in, int ldi, const float* g, const float* b, const float* add, int lda,
+                            float* out, int ldo, int rows, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  LaunchScope ls(KC_LAYERNORM, s);
+  layernorm256_kernel<<<cdiv(rows, 8), 256, 0, s>>>(in, ldi, g, b, add, lda, out, ldo, rows, 1e-6f);
+  LTR_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+#define LTR_TRY(expr)        \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, float* out_rows, const EncodeWs& w,
+                       cudaStream_t s) {
+  const int R = in.n_lines, T = in.n_tokens;
+  const int* cu = in.cu_lines_dev;
+  // ---- token stage, chunked over lines so that h128/h256/x stay L2 resident ----
+  for (int l0 = 0; l0 < R; l0 += w.chunk_lines) {
+    const int nl = std::min(w.chunk_lines, R - l0);
+    const int rows = nl * T;
+    const int64_t t0 = (int64_t)l0 * T;
+    LTR_TRY(launch_small_mlp<true>(m->wpe.head, in.pnt + t0 * 2, in.score + t0, nullptr, w.h128, rows, in.image_width,
+                                   in.image_height, s));
+    LTR_TRY(launch_linear_f32(lin(w.h128, 128, m->wpe.w4, m->wpe.b4, w.h256, 256, rows, 256, 128, ACT_RELU), s));
+    // x = desc + word_position_enc  (line_transformer.py:117)
+    LTR_TRY(launch_linear_f32(lin(w.h256, 256, m->wpe.w5, m->wpe.b5, w.x, 256, rows, 256, 256, ACT_NONE,
+                                  in.desc + t0 * 256, 256), s));
+    {
+      LaunchScope ls(KC_CLS_POOL, s);
+      cls_pool_kernel<<<nl, CP_THREADS, 0, s>>>(w.x, m->U, m->s_cls, m->cls, w.z + (int64_t)l0 * 1024, T);
+      LTR_CUDA_TRY(cudaGetLastError());
+    }
+  }
+  // ---- line stage: V projection per head, fc + CLS residual, LN, FFN, LN, + line pos ----
+  {
+    LinearArgs a = lin(w.z, 1024, m->wv, m->bv, w.ctx, 256, R, 64, 256, ACT_NONE);
+    a.nz = 4; a.sA = 256; a.sW = 64 * 256; a.sB = 64; a.sC = 64;
+    LTR_TRY(launch_linear_f32(a, s));
+  }
+  LTR_TRY(launch_linear_f32(lin(w.ctx, 256, m->wfc, m->bfc, w.y1, 256, R, 256, 256, ACT_NONE), s));
+  LTR_TRY(launch_layernorm(w.y1, 256, m->ln1g, m->ln1b, nullptr, 0, w.y1, 256, R, s));
+  float* g = w.z;  // z is dead after the V projection
+  LTR_TRY(launch_linear_f32(lin(w.y1, 256, m->w1, m->b1, g, 1024, R, 1024, 256, ACT_GELU), s));
+  LTR_TRY(launch_linear_f32(lin(g, 1024, m->w2, m->b2, w.y2, 256, R, 256, 1024, ACT_NONE, w.y1, 256), s));
+  LTR_TRY(launch_small_mlp<false>(m->lpe.head, in.sublines, in.resp, in.angle, w.l128, R, in.image_width,
+                                  in.image_height, s));
+  LTR_TRY(launch_linear_f32(lin(w.l128, 128, m->lpe.w4, m->lpe.b4, w.l256, 256, R, 256, 128, ACT_RELU), s));
+  LTR_TRY(launch_linear_f32(lin(w.l256, 256, m->lpe.w5, m->lpe.b5, w.lpos, 256, R, 256, 256, ACT_NONE), s));
+  // sentence = klines_pos + LN(ffn)  -> xm[:, :256]
+  LTR_TRY(launch_layernorm(w.y2, 256, m->ln2g, m->ln2b, w.lpos, 256, w.xm, 512, R, s));
+  // ---- line signature layers ----
+  int max_l = in.lines_per_image;
+  if (in.cu_lines_host) {
+    max_l = 0;
+    for (int i = 0; i < in.n_images; ++i) max_l = std::max(max_l, in.cu_lines_host[i + 1] - in.cu_lines_host[i]);
+  }
+  for (size_t li = 0; li < m->sig.size(); ++li) {
+    const SigLayer& L = m->sig[li];
+    LTR_TRY(launch_linear_f32(lin(w.xm, 512, L.wqkv, L.bqkv, w.qkv, 768, R, 768, 256, ACT_NONE), s));
+    if (max_l > 0) {
+      LaunchScope ls(KC_SIG_ATTN, s);
+      dim3 grid(cdiv(max_l, SA_THREADS), 4, in.n_images);
+      sig_attention_kernel<<<grid, SA_THREADS, 0, s>>>(w.qkv, w.o, 256, cu, in.lines_per_image);
+      LTR_CUDA_TRY(cudaGetLastError());
+    }
+    LTR_TRY(launch_linear_f32(lin(w.o, 256, L.wm, L.bm, w.xm + 256, 512, R, 256, 256, ACT_NONE), s));
+    LTR_TRY(launch_linear_f32(lin(w.xm, 512, L.w1, L.b1, w.hm, 512, R, 512, 512, ACT_RELU), s));
+    LTR_TRY(launch_linear_f32(lin(w.hm, 512, L.w2, L.b2, w.xm, 512, R, 256, 512, ACT_NONE, w.xm, 512), s));
+  }
+  LTR_TRY(launch_linear_f32(lin(w.xm, 512, m->wf, m->bf, w.yf, 256, R, 256, 256, ACT_NONE), s));
+  if (max_l > 0) {
+    LaunchScope ls(KC_FINAL_NORM, s);
+    dim3 grid(cdiv(max_l, 32), in.n_images);
+    final_norm_kernel<<<grid, 256, 0, s>>>(w.yf, out_rows, out_cf, cu, in.lines_per_image);
+    LTR_CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+static int run_nn(const NNArgs& a, int n_pairs, int max_k0, int max_k1, cudaStream_t s) {
+  LTR_CUDA_TRY(cudaMemsetAsync(a.counts, 0, sizeof(int) * n_pairs, s));
+  if (max_k0 <= 0) return 0;
+  {
+    LaunchScope ls(KC_ARGMIN, s);
+    row_argmin_kernel<<<dim3(cdiv(max_k0, 8), n_pairs), 256, 0, s>>>(a);
+    LTR_CUDA_TRY(cudaGetLastError());
+  }
+  if (a.mutual && max_k1 > 0) {
+    LaunchScope ls(KC_ARGMIN, s);
+    col_argmin_kernel<<<dim3(cdiv(max_k1, 32), n_pairs), 256, 0, s>>>(a);
+    LTR_CUDA_TRY(cudaGetLastError());
+  }
+  {
+    LaunchScope ls(KC_MUTUAL, s);
+    mutual_kernel<<<dim3(cdiv(max_k0, 256), n_pairs), 256, 0, s>>>(a);
+    LTR_CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace ltr
+
+using namespace ltr;
+
+extern "C" {
+
+int ltr_abi_version(void) { return LTR_ABI_VERSION; }
+const char* ltr_last_error(void) { return g_last_error.c_str(); }
+int64_t ltr_launch_count(void) { return g_launches.load(); }
+void ltr_reset_launch_count(void) { g_launches.store(0); }
+
+void ltr_profile_begin(void) {
+  for (auto& r : g_prof.recs) { g_prof.pool.push_back(r.a); g_prof.pool.push_back(r.b); }
+  g_prof.recs.clear();
+  g_prof.on = true;
+}
+
+int ltr_profile_end(const char** names, float* ms, int32_t* launches, int32_t max_classes) {
+  g_prof.on = false;
+  cudaDeviceSynchronize();
+  float tot[KC_COUNT] = {0};
+  int cnt[KC_COUNT] = {0};
+  for (auto& r : g_prof.recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { tot[r.kc] += t; cnt[r.kc]++; }
+    g_prof.pool.push_back(r.a);
+    g_prof.pool.push_back(r.b);
+  }
+  g_prof.recs.clear();
+  int n = 0;
+  for (int k = 0; k < KC_COUNT && n < max_classes; ++k) {
+    if (!cnt[k]) continue;
+    names[n] = kernel_class_name(k);
+    ms[n] = tot[k];
+    launches[n] = cnt[k];
+    ++n;
+  }
+  return n;
+}
+
+int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg, int32_t device, LtrModel** out) {
+  if (!tensors || !cfg || !out) return set_error(LTR_E_INVALID, "ltr_create: null argument");
+  if (cfg->d_model != 256 || cfg->n_heads != 4)
+    return set_error(LTR_E_UNSUPPORTED, "ltr_create: kernels are specialised for d_model=256, n_heads=4");
+  if (cfg->d_inner <= 0 || cfg->d_inner % 64 || cfg->n_desc_layers < 1 || cfg->n_sig_layers < 0)
+    return set_error(LTR_E_INVALID, "ltr_create: bad d_inner / layer counts");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_error(LTR_E_CUDA, "ltr_create: no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_error(LTR_E_INVALID, "ltr_create: bad device index");
+  LTR_CUDA_TRY(cudaSetDevice(device));
+
+  TensorMap tm;
+  for (int i = 0; i < n_tensors; ++i) tm[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+  std::string err;
+  HostPack hp;
+  const int D = 256, DI = cfg->d_inner;
+  MlpOffsets wpe_o{}, lpe_o{};
+  if (!pack_pos_encoder(tm, "klenc.word_position_enc.encoder", 3, hp, wpe_o, err) ||
+      !pack_pos_encoder(tm, "klenc.line_position_enc.encoder", 5, hp, lpe_o, err))
+    return set_error(LTR_E_INVALID, err);
+
+  // ---- descriptive layer (only the last one is live) ----
+  const std::string dl = "klenc.desc_layers." + std::to_string(cfg->n_desc_layers - 1);
+  const float *cls, *wq, *bq, *wk, *bk, *wv, *bv, *wfc, *bfc, *ln1g, *ln1b, *w1, *b1, *w2, *b2, *ln2g, *ln2b;
+  if (!fetch(tm, "klenc.cls_token", D, &cls, err) ||
+      !fetch(tm, dl + ".slf_attn.w_qs.weight", D * D, &wq, err) || !fetch(tm, dl + ".slf_attn.w_qs.bias", D, &bq, err) ||
+      !fetch(tm, dl + ".slf_attn.w_ks.weight", D * D, &wk, err) || !fetch(tm, dl + ".slf_attn.w_ks.bias", D, &bk, err) ||
+      !fetch(tm, dl + ".slf_attn.w_vs.weight", D * D, &wv, err) || !fetch(tm, dl + ".slf_attn.w_vs.bias", D, &bv, err) ||
+      !fetch(tm, dl + ".slf_attn.fc.weight", D * D, &wfc, err) || !fetch(tm, dl + ".slf_attn.fc.bias", D, &bfc, err) ||
+      !fetch(tm, dl + ".slf_attn.layer_norm.weight", D, &ln1g, err) ||
+      !fetch(tm, dl + ".slf_attn.layer_norm.bias", D, &ln1b, err) ||
+      !fetch(tm, dl + ".pos_ffn.w_1.weight", (int64_t)DI * D, &w1, err) || !fetch(tm, dl + ".pos_ffn.w_1.bias", DI, &b1, err) ||
+      !fetch(tm, dl + ".pos_ffn.w_2.weight", (int64_t)D * DI, &w2, err) || !fetch(tm, dl + ".pos_ffn.w_2.bias", D, &b2, err) ||
+      !fetch(tm, dl + ".pos_ffn.layer_norm.weight", D, &ln2g, err) ||
+      !fetch(tm, dl + ".pos_ffn.layer_norm.bias", D, &ln2b, err))
+    return set_error(LTR_E_INVALID, err);
+  (void)bk;  // the key bias shifts all scores of a head equally: cancels in the softmax
+  auto vec = [](const float* p, size_t n) { return std::vector<double>(p, p + n); };
+  // q_cls = W_q cls + b_q ;  u_h = W_k,h^T q_h / sqrt(64) ;  s_cls,h = cls . u_h
+  std::vector<double> q(D), U(4 * D, 0.0), scls(4, 0.0);
+  for (int o = 0; o < D; ++o) {
+    double a = bq[o];
+    for (int i = 0; i < D; ++i) a += (double)wq[o * D + i] * cls[i];
+    q[o] = a;
+  }
+  for (int h = 0; h < 4; ++h) {
+    for (int c = 0; c < D; ++c) {
+      double a = 0;
+      for (int d = 0; d < 64; ++d) a += (double)wk[(h * 64 + d) * D + c] * q[h * 64 + d];
+      U[h * D + c] = a / 8.0;
+    }
+    for (int c = 0; c < D; ++c) scls[h] += (double)cls[c] * U[h * D + c];
+  }
+  std::vector<double> bfc_cls(D);
+  for (int i = 0; i < D; ++i) bfc_cls[i] = (double)bfc[i] + cls[i];  // fc bias + CLS residual (line_attention.py:72)
+  size_t oU = hp.add(U), oS = hp.add(scls), oC = hp.add(vec(cls, D));
+  size_t oWv = hp.add(vec(wv, D * D)), oBv = hp.add(vec(bv, D));
+  size_t oWfc = hp.add(vec(wfc, D * D)), oBfc = hp.add(bfc_cls);
+  size_t oL1g = hp.add(vec(ln1g, D)), oL1b = hp.add(vec(ln1b, D));
+  size_t oW1 = hp.add(vec(w1, (size_t)DI * D)), oB1 = hp.add(vec(b1, DI));
+  size_t oW2 = hp.add(vec(w2, (size_t)D * DI)), oB2 = hp.add(vec(b2, D));
+  size_t oL2g = hp.add(vec(ln2g, D)), oL2b = hp.add(vec(ln2b, D));
+
+  // ---- signature layers ----
+  struct SigOff { size_t wqkv, bqkv, wm, bm, w1, b1, w2, b2; };
+  std::vector<SigOff> so(cfg->n_sig_layers);
+  for (int li = 0; li < cfg->n_sig_layers; ++li) {
+    const std::string p = "selfattn.layers." + std::to_string(li);
+    std::vector<double> Wqkv((size_t)768 * D), bqkv(768);
+    for (int t = 0; t < 3; ++t) {
+      const float *w, *b;
+      if (!fetch(tm, p + ".attn.proj." + std::to_string(t) + ".weight", D * D, &w, err) ||
+          !fetch(tm, p + ".attn.proj." + std::to_string(t) + ".bias", D, &b, err))
+        return set_error(LTR_E_INVALID, err);
+      const double sc = (t == 0) ? 0.125 : 1.0;  // scores / sqrt(64), line_transformer.py:134
+      for (int h = 0; h < 4; ++h)
+        for (int d = 0; d < 64; ++d) {
+          const int oldr = d * 4 + h, newr = t * 256 + h * 64 + d;  // view(b, dim, heads, n), :151
+          for (int i = 0; i < D; ++i) Wqkv[(size_t)newr * D + i] = (double)w[oldr * D + i] * sc;
+          bqkv[newr] = (double)b[oldr] * sc;
+        }
+    }
+    const float *wm, *bm;
+    if (!fetch(tm, p + ".attn.merge.weight", D * D, &wm, err) || !fetch(tm, p + ".attn.merge.bias", D, &bm, err))
+      return set_error(LTR_E_INVALID, err);
+    std::vector<double> Wm((size_t)D * D);
+    for (int o = 0; o < D; ++o)
+      for (int h = 0; h < 4; ++h)
+        for (int d = 0; d < 64; ++d) Wm[(size_t)o * D + h * 64 + d] = wm[o * D + d * 4 + h];
+    std::vector<double> W1, B1, W2, B2;
+    if (!fold_layer(tm, p + ".mlp.0", p + ".mlp.1", 2 * D, 2 * D, W1, B1, err) ||
+        !fold_layer(tm, p + ".mlp.3", "", D, 2 * D, W2, B2, err))
+      return set_error(LTR_E_INVALID, err);
+    so[li] = {hp.add(Wqkv), hp.add(bqkv), hp.add(Wm), hp.add(vec(bm, D)), hp.add(W1), hp.add(B1), hp.add(W2), hp.add(B2)};
+  }
+  std::vector<double> Wf, Bf;
+  if (!fold_layer(tm, "final_proj", "", D, D, Wf, Bf, err)) return set_error(LTR_E_INVALID, err);
+  size_t oWf = hp.add(Wf), oBf = hp.add(Bf);
+
+  LtrModel* m = new LtrModel();
+  m->device = device;
+  m->cfg = *cfg;
+  m->arena_floats = hp.buf.size();
+  cudaError_t ce = cudaMalloc(&m->arena, hp.buf.size() * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMemcpy(m->arena, hp.buf.data(), hp.buf.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    if (m->arena) cudaFree(m->arena);
+    delete m;
+    return set_error(LTR_E_CUDA, std::string("ltr_create: ") + cudaGetErrorString(ce));
+  }
+  float* B = m->arena;
+  bind_mlp(m->wpe, B, wpe_o);
+  bind_mlp(m->lpe, B, lpe_o);
+  m->U = B + oU; m->s_cls = B + oS; m->cls = B + oC;
+  m->wv = B + oWv; m->bv = B + oBv; m->wfc = B + oWfc; m->bfc = B + oBfc;
+  m->ln1g = B + oL1g; m->ln1b = B + oL1b;
+  m->w1 = B + oW1; m->b1 = B + oB1; m->w2 = B + oW2; m->b2 = B + oB2;
+  m->ln2g = B + oL2g; m->ln2b = B + oL2b;
+  for (auto& o : so) m->sig.push_back({B + o.wqkv, B + o.bqkv, B + o.wm, B + o.bm, B + o.w1, B + o.b1, B + o.w2, B + o.b2});
+  m->wf = B + oWf; m->bf = B + oBf;
+  if (const char* e = std::getenv("LINETR_TOKEN_CHUNK")) {
+    int v = std::atoi(e);
+    if (v > 0) m->token_chunk = v;
+  }
+  *out = m;
+  return LTR_OK;
+}
+
+void ltr_destroy(LtrModel* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->arena) cudaFree(m->arena);
+  delete m;
+}
+
+int64_t ltr_encode_workspace_bytes(const LtrModel* m, int32_t n_images, int32_t n_lines, int32_t n_tokens) {
+  (void)n_images;
+  if (!m || n_lines < 0 || n_tokens < 1) return set_error(LTR_E_INVALID, "ltr_encode_workspace_bytes: bad argument");
+  return carve(m, n_lines, n_tokens, nullptr).bytes + 256;
+}
+
+int ltr_encode(LtrModel* m, const LtrEncodeInput* in, float* desc_cf_out, float* desc_rows_out, void* workspace,
+               int64_t workspace_bytes, void* stream) {
+  if (!m || !in) return set_error(LTR_E_INVALID, "ltr_encode: null argument");
+  if (in->n_lines == 0 || in->n_images == 0) return LTR_OK;
+  if (in->n_tokens < 1 || in->n_tokens > 128) return set_error(LTR_E_UNSUPPORTED, "ltr_encode: n_tokens must be in 1..128");
+  if (!in->sublines || !in->resp || !in->angle || !in->pnt || !in->desc || !in->score)
+    return set_error(LTR_E_INVALID, "ltr_encode: null input tensor");
+  if ((in->cu_lines_host == nullptr) != (in->cu_lines_dev == nullptr))
+    return set_error(LTR_E_INVALID, "ltr_encode: cu_lines_host and cu_lines_dev must be given together");
+  if (!in->cu_lines_host && (int64_t)in->lines_per_image * in->n_images != in->n_lines)
+    return set_error(LTR_E_INVALID, "ltr_encode: uniform batch needs n_lines == n_images * lines_per_image");
+  if (in->cu_lines_host && (in->cu_lines_host[0] != 0 || in->cu_lines_host[in->n_images] != in->n_lines))
+    return set_error(LTR_E_INVALID, "ltr_encode: cu_lines must start at 0 and end at n_lines");
+  if (!(in->image_width > 0.f) || !(in->image_height > 0.f)) return set_error(LTR_E_INVALID, "ltr_encode: bad image shape");
+  LTR_CUDA_TRY(cudaSetDevice(m->device));
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(workspace), 256));
+  EncodeWs w = carve(m, in->n_lines, in->n_tokens, base);
+  if (!workspace || (base - (char*)workspace) + w.bytes > workspace_bytes)
+    return set_error(LTR_E_WORKSPACE, "ltr_encode: workspace too small, need " + std::to_string(w.bytes + 256));
+  return encode_impl(m, *in, desc_cf_out, desc_rows_out, w, as_stream(stream));
+}
+
+int ltr_match(const LtrMatchInput* in, const LtrMatchOutput* out, int32_t device, void* stream) {
+  if (!in || !out) return set_error(LTR_E_INVALID, "ltr_match: null argument");
+  if (in->n_pairs <= 0) return LTR_OK;
+  if (!out->matches0 || !out->scores0 || !out->nn1 || !out->counts || !out->dist_key)
+    return set_error(LTR_E_INVALID, "ltr_match: matches0, scores0, nn1, counts and dist_key are required");
+  if (in->d <= 0 || in->d % 16) return set_error(LTR_E_UNSUPPORTED, "ltr_match: descriptor dim must be a multiple of 16");
+  const bool seg = in->sub_off0 != nullptr || in->sub_off1 != nullptr;
+  if (seg && (!in->sub_off0 || !in->sub_off1 || !in->cuk0 || !in->cuk1 || !in->cu0 || !in->cu1 || !out->dist_sub))
+    return set_error(LTR_E_INVALID, "ltr_match: keyline merging needs sub_off0/1, cuk0/1, cu0/1 and dist_sub");
+  if ((in->cu0 == nullptr) != (in->cu1 == nullptr)) return set_error(LTR_E_INVALID, "ltr_match: cu0/cu1 must be given together");
+  LTR_CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = as_stream(stream);
+  const int mx0 = in->cu0 ? in->max_n0 : in->n0, mx1 = in->cu1 ? in->max_n1 : in->n1;
+  const int mk0 = seg ? in->max_k0 : mx0, mk1 = seg ? in->max_k1 : mx1;
+  const long long stride_key = in->dist_pair_stride > 0 ? in->dist_pair_stride : (long long)mk0 * mk1;
+  if (mx0 > 0 && mx1 > 0) {
+    if (!in->desc0 || !in->desc1) return set_error(LTR_E_INVALID, "ltr_match: null descriptors");
+    DistArgs da{};
+    da.d0 = in->desc0; da.d1 = in->desc1; da.layout = in->layout; da.d = in->d;
+    da.cu0 = in->cu0; da.cu1 = in->cu1; da.n0 = in->n0; da.n1 = in->n1;
+    da.out = seg ? out->dist_sub : out->dist_key;
+    da.stride = seg ? (long long)mx0 * mx1 : stride_key;
+    dim3 grid(cdiv(mx0, DK_BM), cdiv(mx1, DK_BN), in->n_pairs);
+    {
+      LaunchScope ls(KC_DIST, s);
+      if (in->layout == LTR_LAYOUT_CHANNEL_FIRST) dist_kernel<true><<<grid, DK_THREADS, 0, s>>>(da);
+      else dist_kernel<false><<<grid, DK_THREADS, 0, s>>>(da);
+      LTR_CUDA_TRY(cudaGetLastError());
+    }
+    if (seg && mk0 > 0 && mk1 > 0) {
+      SegMeanArgs sa{out->dist_sub, (long long)mx0 * mx1, out->dist_key, stride_key, in->cuk0, in->cuk1, in->sub_off0, in->sub_off1};
+      LaunchScope ls(KC_SEGMEAN, s);
+      segmean_kernel<<<dim3(cdiv(mk1, 32), cdiv(mk0, 8), in->n_pairs), 256, 0, s>>>(sa);
+      LTR_CUDA_TRY(cudaGetLastError());
+    }
+  }
+  NNArgs na{};
+  na.dist = out->dist_key; na.stride = stride_key;
+  na.cuk0 = seg ? in->cuk0 : in->cu0; na.cuk1 = seg ? in->cuk1 : in->cu1;
+  na.n0 = in->n0; na.n1 = in->n1; na.thr = in->nn_thresh; na.mutual = in->mutual;
+  na.matches0 = out->matches0; na.scores0 = out->scores0; na.nn1 = out->nn1; na.counts = out->counts;
+  return run_nn(na, in->n_pairs, mk0, mk1, s);
+}
+
+int ltr_match_distmat(const float* dist, int32_t n_pairs, int32_t n0, int32_t n1, int64_t dist_pair_stride, float nn_thresh,
+                      int32_t mutual, int32_t* matches0, float* scores0, int32_t* nn1, int32_t* counts, int32_t device,
+                      void* stream) {
+  if (n_pairs <= 0) return LTR_OK;
+  if (!matches0 || !scores0 || !nn1 || !counts) return set_error(LTR_E_INVALID, "ltr_match_distmat: null output");
+  if (n0 > 0 && n1 > 0 && !dist) return set_error(LTR_E_INVALID, "ltr_match_distmat: null distance matrix");
+  LTR_CUDA_TRY(cudaSetDevice(device));
+  NNArgs na{};
+  na.dist = dist; na.stride = dist_pair_stride > 0 ? dist_pair_stride : (long long)n0 * n1;
+  na.n0 = n0; na.n1 = n1; na.thr = nn_thresh; na.mutual = mutual;
+  na.matches0 = matches0; na.scores0 = scores0; na.nn1 = nn1; na.counts = counts;
+  return run_nn(na, n_pairs, n0, n1, as_stream(stream));
+}
+
+int ltr_merge_sublines(const float* dist_sub, int64_t stride_sub, int32_t n_pairs, const int32_t* cuk0,
+                       const int32_t* cuk1, const int32_t* sub_off0, const int32_t* sub_off1, int32_t max_k0,
+                       int32_t max_k1, float* dist_key, int64_t stride_key, int32_t device, void* stream) {
+  if (n_pairs <= 0 || max_k0 <= 0 || max_k1 <= 0) return LTR_OK;
+  if (!dist_sub || !cuk0 || !cuk1 || !sub_off0 || !sub_off1 || !dist_key)
+    return set_error(LTR_E_INVALID, "ltr_merge_sublines: null argument");
+  LTR_CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = as_stream(stream);
+  SegMeanArgs sa{dist_sub, stride_sub, dist_key, stride_key, cuk0, cuk1, sub_off0, sub_off1};
+  LaunchScope ls(KC_SEGMEAN, s);
+  segmean_kernel<<<dim3(cdiv(max_k1, 32), cdiv(max_k0, 8), n_pairs), 256, 0, s>>>(sa);
+  LTR_CUDA_TRY(cudaGetLastError());
+  return LTR_OK;
+}
+
+int ltr_linear(const float* x, int32_t ldx, const float* w, const float* bias, const float* res, int32_t ldr, float* y,
+               int32_t ldy, int32_t m, int32_t n, int32_t k, int32_t act, int32_t device, void* stream) {
+  if (!x || !w || !y) return set_error(LTR_E_INVALID, "ltr_linear: null argument");
+  LTR_CUDA_TRY(cudaSetDevice(device));
+  return launch_linear_f32(lin(x, ldx, w, bias, y, ldy, m, n, k, act, res, ldr), as_stream(stream));
+}
+
+}  // extern "C"

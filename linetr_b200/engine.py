@@ -1,0 +1,235 @@
+"""Batched front-end of the hot path: many image pairs per call, everything on the device.
+
+The reference's `Matching.forward` (models/matching.py:18-86) handles ONE pair per call and
+round-trips through host numpy between descriptor forward, distance matrix, subline merge
+and matcher (matching.py:69-84).  `PairEngine.match_pairs` runs the same line branch
+(matching.py:77-81) for a whole batch of independent pairs: two `ltr_encode` calls (side 0,
+side 1; images of different line counts are handled with `cu_lines`, never by padding - the
+signature attention has no mask) and one `ltr_match`.
+
+Pairs are independent, so multi-GPU use is plain sharding (`shard_range`) plus one
+all-gather of the per-pair match counts (`gather_counts`); see DESIGN.md §multi-GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import _ops
+
+_KEYS = ("sublines", "resp_sublines", "angle_sublines", "pnt_sublines", "desc_sublines", "score_sublines")
+
+
+@dataclass
+class LineBatch:
+    """Tokenised lines of a batch of images, rows of all images concatenated.
+
+    sublines [R,2,2], resp [R,1], angle [R,2], pnt [R,T,2], desc [R,T,256], score [R,T,1];
+    cu_lines: np.int32 [n_images+1] line offsets.  Optional key-line structure for
+    subline->keyline merging: sub_off np.int32 [n_keylines+1] (CSR, global subline numbering)
+    and cuk np.int32 [n_images+1]; None means every subline is its own key line.
+    """
+    sublines: torch.Tensor
+    resp: torch.Tensor
+    angle: torch.Tensor
+    pnt: torch.Tensor
+    desc: torch.Tensor
+    score: torch.Tensor
+    cu_lines: np.ndarray
+    sub_off: Optional[np.ndarray] = None
+    cuk: Optional[np.ndarray] = None
+    _dev_cache: dict = field(default_factory=dict, repr=False)
+
+    @property
+    def n_images(self) -> int:
+        return len(self.cu_lines) - 1
+
+    @property
+    def n_lines(self) -> int:
+        return int(self.cu_lines[-1])
+
+    @property
+    def n_tokens(self) -> int:
+        return int(self.desc.shape[1])
+
+    @property
+    def uniform_lines(self) -> Optional[int]:
+        d = np.diff(self.cu_lines)
+        return int(d[0]) if len(d) and bool((d == d[0]).all()) else None
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.tensors())
+
+    def tensors(self):
+        return (self.sublines, self.resp, self.angle, self.pnt, self.desc, self.score)
+
+    @staticmethod
+    def from_stacked(data: dict) -> "LineBatch":
+        """From the reference's stacked dict layout [B,L,...] (line_process.py:182-193)."""
+        B, L = int(data["desc_sublines"].shape[0]), int(data["desc_sublines"].shape[1])
+        T = int(data["desc_sublines"].shape[2])
+        f = lambda k, *s: torch.as_tensor(data[k]).float().reshape(B * L, *s).contiguous()
+        return LineBatch(f("sublines", 2, 2), f("resp_sublines", 1), f("angle_sublines", 2), f("pnt_sublines", T, 2),
+                         f("desc_sublines", T, 256), f("score_sublines", T, 1),
+                         (np.arange(B + 1, dtype=np.int64) * L).astype(np.int32))
+
+    @staticmethod
+    def from_images(images: Sequence[dict]) -> "LineBatch":
+        """From per-image tokenizer dicts (batch dim 1 each); line counts may differ.  Uses
+        'mat_klines2sublines' (if present and not the identity) to build the key-line CSR."""
+        from .nn_matcher import adjacency_to_csr
+        T = int(images[0]["desc_sublines"].shape[2])
+        cat = lambda k, *s: torch.cat([torch.as_tensor(im[k])[0].float().reshape(-1, *s) for im in images], 0).contiguous()
+        counts = [int(im["desc_sublines"].shape[1]) for im in images]
+        cu = np.zeros(len(images) + 1, dtype=np.int32)
+        cu[1:] = np.cumsum(counts)
+        sub_off = cuk = None
+        if all("mat_klines2sublines" in im for im in images):
+            offs, nk, merged = [], [], False
+            for im, base in zip(images, cu[:-1]):
+                A = im["mat_klines2sublines"]
+                A = A.detach().cpu().numpy() if isinstance(A, torch.Tensor) else np.asarray(A)
+                o = adjacency_to_csr(A[0])
+                merged |= len(o) - 1 != o[-1]
+                offs.append(o[:-1].astype(np.int64) + int(base))
+                nk.append(len(o) - 1)
+            if merged:
+                sub_off = np.concatenate(offs + [np.array([cu[-1]], dtype=np.int64)]).astype(np.int32)
+                cuk = np.zeros(len(images) + 1, dtype=np.int32)
+                cuk[1:] = np.cumsum(nk)
+        return LineBatch(cat("sublines", 2, 2), cat("resp_sublines", 1), cat("angle_sublines", 2),
+                         cat("pnt_sublines", T, 2), cat("desc_sublines", T, 256), cat("score_sublines", T, 1),
+                         cu, sub_off, cuk)
+
+    def pin(self) -> "LineBatch":
+        return LineBatch(*[t.pin_memory() for t in self.tensors()], self.cu_lines, self.sub_off, self.cuk)
+
+    def to(self, device, non_blocking=True) -> "LineBatch":
+        return LineBatch(*[t.to(device, non_blocking=non_blocking) for t in self.tensors()], self.cu_lines,
+                         self.sub_off, self.cuk)
+
+    def dev_i32(self, name: str, device) -> torch.Tensor:
+        key = (name, str(device))
+        if key not in self._dev_cache:
+            self._dev_cache[key] = torch.from_numpy(np.ascontiguousarray(getattr(self, name), dtype=np.int32)).to(device)
+        return self._dev_cache[key]
+
+
+def merge_sublines(dist_sub: torch.Tensor, sub_off0: torch.Tensor, sub_off1: torch.Tensor, K0: int, K1: int):
+    """A0 @ D @ A1^T for ONE pair on the GPU (ltr_merge_sublines); dist_sub [S0,S1] CUDA."""
+    dev = dist_sub.device
+    dist_sub = dist_sub.float().contiguous()
+    cuk0 = torch.tensor([0, K0], dtype=torch.int32, device=dev)
+    cuk1 = torch.tensor([0, K1], dtype=torch.int32, device=dev)
+    out = torch.empty((K0, K1), dtype=torch.float32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    with torch.cuda.device(dev):
+        rc = N.load().ltr_merge_sublines(p(dist_sub), 0, 1, p(cuk0), p(cuk1), p(sub_off0.int().contiguous()),
+                                         p(sub_off1.int().contiguous()), K0, K1, p(out), 0, dev.index,
+                                         C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    N.check(rc, "ltr_merge_sublines")
+    return out
+
+
+@dataclass
+class PairMatches:
+    matches0: torch.Tensor     # int32 [total key lines side 0]: index in side 1 (local to the pair) or -1
+    scores0: torch.Tensor      # float32, distance to the nearest neighbour
+    counts: torch.Tensor       # int32 [n_pairs]
+    offsets0: np.ndarray       # int32 [n_pairs+1] key-line offsets of side 0 into matches0
+    dist: torch.Tensor         # float32 flat, pair p at p*stride, row-major [K0_p, K1_p]
+    stride: int
+    desc0: Optional[torch.Tensor] = None   # [R0,256] unit descriptors (rows)
+    desc1: Optional[torch.Tensor] = None
+
+    def pair(self, p: int) -> torch.Tensor:
+        return self.matches0[int(self.offsets0[p]):int(self.offsets0[p + 1])]
+
+
+class PairEngine:
+    """Batched line-descriptor forward + mutual-NN matching on one GPU."""
+
+    def __init__(self, model, device=None):
+        self.model = model
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise N.LtrError("PairEngine needs a CUDA device (there is no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def encode(self, batch: LineBatch, want_cf=False) -> torch.Tensor:
+        """-> unit descriptors [R,256] (rows); with want_cf also the flat channel-first layout."""
+        h = self.model._get_handle(self.device)
+        L = batch.uniform_lines
+        kw = dict(lines_per_image=L) if L is not None and L > 0 else dict(
+            cu_lines_host=batch.cu_lines, cu_lines_dev=batch.dev_i32("cu_lines", self.device))
+        cf, rows = _ops.encode(h, batch.sublines, batch.resp, batch.angle, batch.pnt, batch.desc, batch.score,
+                               self.model._image_wh(), want_cf=want_cf, want_rows=True, **kw)
+        return (rows, cf) if want_cf else rows
+
+    def match_pairs(self, side0: LineBatch, side1: LineBatch, nn_thresh: Optional[float] = None, mutual=True,
+                    keep_desc=False) -> PairMatches:
+        if side0.n_images != side1.n_images:
+            raise ValueError("match_pairs: both sides need the same number of images")
+        if nn_thresh is None:
+            nn_thresh = self.model.config.get("nn_threshold", 0.8)
+        P = side0.n_images
+        d0 = self.encode(side0)
+        d1 = self.encode(side1)
+        seg = side0.sub_off is not None or side1.sub_off is not None
+        L0, L1 = side0.uniform_lines, side1.uniform_lines
+        kw = {}
+        if seg:
+            def csr(b):
+                if b.sub_off is None:  # identity on this side
+                    b.sub_off = np.arange(b.n_lines + 1, dtype=np.int32)
+                    b.cuk = b.cu_lines.copy()
+                return b.dev_i32("sub_off", self.device), b.dev_i32("cuk", self.device)
+            so0, ck0 = csr(side0)
+            so1, ck1 = csr(side1)
+            kw = dict(cu0=side0.dev_i32("cu_lines", self.device), cu1=side1.dev_i32("cu_lines", self.device),
+                      max_n0=int(np.diff(side0.cu_lines).max(initial=0)), max_n1=int(np.diff(side1.cu_lines).max(initial=0)),
+                      sub_off0=so0, sub_off1=so1, cuk0=ck0, cuk1=ck1,
+                      max_k0=int(np.diff(side0.cuk).max(initial=0)), max_k1=int(np.diff(side1.cuk).max(initial=0)),
+                      total_k0=int(side0.cuk[-1]), total_k1=int(side1.cuk[-1]))
+            off0 = side0.cuk
+        elif L0 is not None and L1 is not None:
+            kw = dict(n0=L0, n1=L1)
+            off0 = side0.cu_lines
+        else:
+            kw = dict(cu0=side0.dev_i32("cu_lines", self.device), cu1=side1.dev_i32("cu_lines", self.device),
+                      max_n0=int(np.diff(side0.cu_lines).max(initial=0)), max_n1=int(np.diff(side1.cu_lines).max(initial=0)),
+                      total_k0=side0.n_lines, total_k1=side1.n_lines)
+            off0 = side0.cu_lines
+        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, **kw)
+        return PairMatches(out["matches0"], out["scores0"], out["counts"], np.asarray(off0, dtype=np.int32),
+                           out["dist_key"], out["stride"], d0 if keep_desc else None, d1 if keep_desc else None)
+
+
+# ------------------------------------------------------------------------------- multi-GPU
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous block of items owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_counts(local_counts: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """The path's one collective: all-gather of per-pair match counts (int32) so that every
+    rank knows the global result size.  Works with NCCL (CUDA tensors) and gloo (CPU)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_counts.clone()
+    world = dist.get_world_size(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    width = max(e - s for s, e in sizes)
+    buf = torch.zeros(width, dtype=torch.int32, device=local_counts.device)
+    buf[:local_counts.numel()] = local_counts
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    return torch.cat([g[:e - s] for g, (s, e) in zip(gathered, sizes)])

@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the numpy oracle, the committed
+reference outputs (tests/golden) and size-independent properties at full BASELINE sizes.
+
+Tolerances: descriptors 1e-3 abs (BASELINE.json north_star; we assert a 10x tighter 1e-4
+where the path is fp32 end to end), match indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from linetr_b200 import _native as N
+from linetr_b200 import _ops, engine, synthetic as syn
+from linetr_b200 import nn_matcher as nnm
+from linetr_b200.line_process import get_dist_matrix
+from linetr_b200.line_transformer import LineTransformer
+from oracle import linetr_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DESC_TOL = 1e-3          # the contract
+DESC_TOL_TIGHT = 2e-4    # what we hold ourselves to
+DEV = torch.device("cuda", 0)
+_models = {}
+
+
+def model_for(tag):
+    if tag not in _models:
+        if tag == "shipped":
+            sd = H.load_shipped_weights()
+            if sd is None:
+                pytest.skip("shipped checkpoint not available")
+            nd = 1
+        else:
+            sd = H.weights_for(tag)
+            nd = int(tag.split(":")[2])
+        m = LineTransformer({"mode": "train", "n_line_descriptive_layers": nd})
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+        _models[tag] = (m.eval().to(DEV), sd)
+    return _models[tag]
+
+
+def to_dev(d):
+    return {k: torch.from_numpy(v).to(DEV) for k, v in d.items()}
+
+
+def fwd(model, data_np):
+    return model(to_dev(data_np))["line_desc"].cpu().numpy()
+
+
+# ------------------------------------------------------------------ GEMM engine
+@pytest.mark.parametrize("M,N_,K,act", [(1, 64, 16, 0), (127, 256, 128, 1), (300, 768, 256, 0), (513, 1024, 256, 2),
+                                        (64, 256, 1024, 0), (2816, 256, 256, 0)])
+def test_linear_engine_vs_torch_fp32(M, N_, K, act):
+    g = torch.Generator().manual_seed(M * 7 + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N_, K, generator=g) / K ** 0.5
+    b = torch.randn(N_, generator=g)
+    r = torch.randn(M, N_, generator=g)
+    want = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    want = [want, torch.relu(want), torch.nn.functional.gelu(want)][act] + r.double()
+    got = _ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), r.to(DEV), act).cpu().double()
+    assert (got - want).abs().max().item() < 2e-5
+
+
+# ------------------------------------------------------------------ encoder
+@pytest.mark.parametrize("name", H.ENC_CASES)
+def test_forward_vs_reference_golden_and_oracle(name):
+    npz, meta = H.golden()
+    case = meta["cases"][name]
+    model, sd = model_for(case["weights"])
+    data = H.case_inputs(case)
+    got = fwd(model, data)
+    assert got.shape == npz[name].shape
+    assert np.abs(got - npz[name]).max() < DESC_TOL_TIGHT           # committed reference output
+    assert np.abs(got - orc.line_transformer_forward(sd, data)).max() < DESC_TOL_TIGHT
+    assert np.abs(np.linalg.norm(got, axis=1) - 1).max() < 1e-5
+
+
+def test_forward_batched_and_inplace_contract():
+    npz, meta = H.golden()
+    case = meta["cases"]["enc_B2_L12_T21"]
+    model, _ = model_for(case["weights"])
+    data = to_dev(H.stack([syn.make_image_inputs(s, case["L"], case["T"], tuple(case["ntok"])) for s in case["seeds"]]))
+    before = {k: v.clone() for k, v in data.items()}
+    out = model(data)
+    assert out is data and "line_desc" in data            # same dict object, updated in place
+    for k, v in before.items():
+        assert torch.equal(v, data[k]), f"forward mutated input {k}"
+    assert tuple(data["line_desc"].shape) == (2, 256, 12) and data["line_desc"].is_cuda
+    assert np.abs(data["line_desc"].cpu().numpy() - npz["enc_B2_L12_T21"]).max() < DESC_TOL_TIGHT
+
+
+def test_mask_is_dead_and_padding_is_live():
+    """the token mask cannot change the output, the content of padded
+    token slots does (they are attended to as real keys)."""
+    model, sd = model_for("synthetic:0:1")
+    d = syn.make_image_inputs(77, 10, 21, (3, 10))
+    base = fwd(model, d)
+    d2 = {k: v.copy() for k, v in d.items()}
+    d2["mask_sublines"] = np.ones_like(d["mask_sublines"])
+    assert np.array_equal(fwd(model, d2), base)
+    d3 = {k: v.copy() for k, v in d.items()}
+    d3["desc_sublines"][0, :, 15:] = 0.0
+    got = fwd(model, d3)
+    assert np.abs(got - base).max() > 1e-3
+    assert np.abs(got - orc.line_transformer_forward(sd, d3)).max() < DESC_TOL_TIGHT
+
+
+def test_varlen_batch_equals_per_image():
+    """Images with different line counts in one call (cu_lines) == one call per image;
+    zero-padding would change the result."""
+    model, sd = model_for("synthetic:0:1")
+    ims = [syn.make_image_inputs(100 + i, L, 21, (2, 21)) for i, L in enumerate((7, 33, 1, 150, 64))]
+    eng = engine.PairEngine(model, DEV)
+    batch = engine.LineBatch.from_images(ims).to(DEV)
+    rows, cf = eng.encode(batch, want_cf=True)
+    rows, cf = rows.cpu().numpy(), cf.cpu().numpy()
+    for i, im in enumerate(ims):
+        want = orc.line_transformer_forward(sd, im)[0]          # [256, L]
+        s, e = batch.cu_lines[i], batch.cu_lines[i + 1]
+        assert np.abs(rows[s:e].T - want).max() < DESC_TOL_TIGHT
+        assert np.abs(cf[256 * s:256 * e].reshape(256, e - s) - want).max() < DESC_TOL_TIGHT
+
+
+def test_token_chunking_is_invisible(monkeypatch):
+    """The token stage is processed in L2-sized chunks of lines; chunk size must not matter."""
+    sd = syn.make_state_dict(0, 1)
+    data = syn.make_image_inputs(5, 50, 21)
+    outs = []
+    for chunk in ("64", "1000000"):
+        monkeypatch.setenv("LINETR_TOKEN_CHUNK", chunk)
+        m = LineTransformer({"mode": "train"})
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        outs.append(fwd(m.eval().to(DEV), data))
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_weight_update_repacks():
+    model, sd = model_for("synthetic:0:1")
+    m = LineTransformer({"mode": "train"})
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.eval().to(DEV)
+    d = syn.make_image_inputs(9, 6, 21)
+    a = fwd(m, d)
+    sd2 = syn.make_state_dict(1, 1)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd2.items()})
+    b = fwd(m, d)
+    assert np.abs(b - orc.line_transformer_forward(sd2, d)).max() < DESC_TOL_TIGHT
+    assert np.abs(a - b).max() > 1e-2
+
+
+# ------------------------------------------------------------------ matcher
+def test_nn_matcher_golden_exact():
+    npz, _ = H.golden()
+    e0, e1, _ = syn.make_descriptor_pair(51, 64, 48)
+    for mutual in (True, False):
+        mat, dist = nnm.nn_matcher(e0, e1, 0.8, mutual)
+        assert mat.dtype == np.float64 and mat.shape == (1, 64, 48) and dist.dtype == np.float32
+        assert np.array_equal(mat, npz[f"nn_64_48_mat_m{int(mutual)}"])
+        assert np.abs(dist - npz["nn_64_48_dist"]).max() < 2e-6
+    mat, _ = nnm.nn_matcher(e0, e1, 0.05, True)
+    assert np.array_equal(mat, npz["nn_64_48_mat_thr005"])
+
+
+def test_distmat_ties_clip_threshold_exact():
+    npz, _ = H.golden()
+    for mutual in (True, False):
+        got = nnm.nn_matcher_distmat(npz["distmat_ties_in"], 0.5, mutual)
+        assert np.array_equal(got, npz[f"distmat_ties_mat_m{int(mutual)}"])
+
+
+@pytest.mark.parametrize("n0,n1", [(1, 1), (1, 40), (33, 1), (257, 300), (1000, 999)])
+def test_distmat_random_vs_oracle_exact(n0, n1):
+    rng = np.random.Generator(np.random.PCG64(n0 * 1000 + n1))
+    # quantised values -> many exact ties; some negatives -> clip
+    d = (rng.integers(-2, 40, size=(1, n0, n1)) / 16.0).astype(np.float32)
+    for mutual in (True, False):
+        for thr in (0.5, 0.0, 10.0):
+            assert np.array_equal(nnm.nn_matcher_distmat(d, thr, mutual), orc.nn_matcher_distmat(d, thr, mutual))
+
+
+def test_get_dist_matrix_and_s2k_golden():
+    npz, meta = H.golden()
+    c = meta["cases"]["s2k"]
+    f0, f1, _ = syn.make_descriptor_pair(c["seed"], sum(c["nsub0"]), sum(c["nsub1"]))
+    dist = get_dist_matrix(f0[None], f1[None])
+    assert dist.dtype == np.float32 and np.abs(dist[0] - npz["s2k_dist_sub"]).max() < 2e-6
+
+    def adj(ns):
+        A = np.zeros((len(ns), sum(ns)), dtype=np.float32)
+        s = 0
+        for i, n in enumerate(ns):
+            A[i, s:s + n] = 1.0 / n
+            s += n
+        return torch.from_numpy(A)
+    m = LineTransformer({"mode": "train"})
+    dk = m.subline2keyline(npz["s2k_dist_sub"], adj(c["nsub0"]), adj(c["nsub1"]))
+    assert dk.shape == npz["s2k_dist_key"].shape and np.abs(dk - npz["s2k_dist_key"]).max() < 2e-6
+    assert np.array_equal(nnm.nn_matcher_distmat(dk, 0.8, True), npz["s2k_mat"])
+    eye = m.subline2keyline(npz["s2k_dist_sub"], torch.eye(sum(c["nsub0"])), torch.eye(sum(c["nsub1"])))
+    assert np.array_equal(eye[0], npz["s2k_dist_sub"])
+
+
+def test_pair_pipeline_vs_reference_golden():
+    npz, meta = H.golden()
+    case = meta["cases"]["pair_L32_27"]
+    model, sd = model_for(case["weights"])
+    a, b, _ = syn.make_pair_inputs(case["seed"], case["L0"], case["T"], n_lines1=case["L1"],
+                                   n_real_tokens=tuple(case["ntok"]))
+    eng = engine.PairEngine(model, DEV)
+    res = eng.match_pairs(engine.LineBatch.from_images([a]).to(DEV), engine.LineBatch.from_images([b]).to(DEV),
+                          case["thr"], keep_desc=True)
+    want_idx = orc.match_indices(npz["pair_L32_27_mat"])
+    assert np.array_equal(res.pair(0).cpu().numpy(), want_idx)
+    assert int(res.counts[0]) == case["n_matches"]
+    assert np.abs(res.desc0.cpu().numpy().T - npz["pair_L32_27_d0"][0]).max() < DESC_TOL_TIGHT
+    dist = res.dist[:32 * 27].view(32, 27).cpu().numpy()
+    assert np.abs(dist - npz["pair_L32_27_dist"][0]).max() < 1e-3
+
+
+def test_pair_batch_with_keyline_merging_vs_oracle():
+    """Several pairs at once, ragged line counts, some key lines split into sublines."""
+    model, sd = model_for("synthetic:0:1")
+    rng = np.random.Generator(np.random.PCG64(5))
+    pairs = []
+    for p in range(3):
+        L = int(rng.integers(12, 40))
+        a, b, _ = syn.make_pair_inputs(200 + p, L, 21, n_lines1=L - int(rng.integers(0, 4)))
+        for side in (a, b):
+            S = side["desc_sublines"].shape[1]
+            ns, left = [], S
+            while left > 0:
+                n = int(min(left, rng.integers(1, 4)))
+                ns.append(n)
+                left -= n
+            A = np.zeros((len(ns), S), np.float32)
+            s = 0
+            for i, n in enumerate(ns):
+                A[i, s:s + n] = 1.0 / n
+                s += n
+            side["mat_klines2sublines"] = A[None]
+        pairs.append((a, b))
+    eng = engine.PairEngine(model, DEV)
+    res = eng.match_pairs(engine.LineBatch.from_images([a for a, _ in pairs]).to(DEV),
+                          engine.LineBatch.from_images([b for _, b in pairs]).to(DEV), 0.8)
+    for p, (a, b) in enumerate(pairs):
+        mat, dk, _, _ = orc.match_pair(sd, a, b, 0.8)
+        assert np.array_equal(res.pair(p).cpu().numpy(), orc.match_indices(mat)), f"pair {p}"
+        assert int(res.counts[p]) == int(mat.sum())
+        K0, K1 = dk.shape[1:]
+        got = res.dist[p * res.stride:p * res.stride + K0 * K1].view(K0, K1).cpu().numpy()
+        assert np.abs(got - dk[0]).max() < 1e-3
+
+
+def test_shipped_checkpoint_cfg1_pair():
+    npz, meta = H.golden()
+    model, sd = model_for("shipped")
+    case = meta["cases"]["real_enc_L16_T21"]
+    assert np.abs(fwd(model, H.case_inputs(case)) - npz["real_enc_L16_T21"]).max() < DESC_TOL_TIGHT
+    case = meta["cases"]["real_pair_L128"]
+    a, b, _ = syn.make_pair_inputs(case["seed"], case["L"], case["T"])
+    eng = engine.PairEngine(model, DEV)
+    res = eng.match_pairs(engine.LineBatch.from_images([a]).to(DEV), engine.LineBatch.from_images([b]).to(DEV),
+                          case["thr"], keep_desc=True)
+    assert np.abs(res.desc0.cpu().numpy().T - npz["real_pair_L128_d0"][0]).max() < DESC_TOL_TIGHT
+    assert np.abs(res.desc1.cpu().numpy().T - npz["real_pair_L128_d1"][0]).max() < DESC_TOL_TIGHT
+    assert np.array_equal(res.pair(0).cpu().numpy(), npz["real_pair_L128_mat_idx"])
+    assert int(res.counts[0]) == case["n_matches"]
+
+
+# ------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("L,T,P", [(128, 21, 8), (256, 32, 4)])
+def test_full_size_properties(L, T, P):
+    """BASELINE cfg[1]/cfg[2] shapes: unit norm, line-permutation equivariance of the encoder,
+    and the matcher recovering the known permutation between the two sides."""
+    model, sd = model_for("synthetic:0:1")
+    eng = engine.PairEngine(model, DEV)
+    sides, perms = ([], []), []
+    for p in range(P):
+        a, b, perm = syn.make_pair_inputs(300 + p, L, T)
+        sides[0].append(a)
+        sides[1].append(b)
+        perms.append(perm)
+    b0 = engine.LineBatch.from_images(sides[0]).to(DEV)
+    b1 = engine.LineBatch.from_images(sides[1]).to(DEV)
+    res = eng.match_pairs(b0, b1, 0.8, keep_desc=True)
+    d0 = res.desc0.cpu().numpy()
+    assert np.abs(np.linalg.norm(d0, axis=1) - 1).max() < 1e-5
+    # one pair against the oracle at full size
+    mat, _, o0, _ = orc.match_pair(sd, sides[0][0], sides[1][0], 0.8)
+    assert np.abs(d0[:L].T - o0[0]).max() < DESC_TOL_TIGHT
+    assert np.array_equal(res.pair(0).cpu().numpy(), orc.match_indices(mat))
+    # permutation equivariance: shuffling the lines of an image shuffles its descriptors
+    rng = np.random.Generator(np.random.PCG64(1))
+    shuf = rng.permutation(L)
+    im = {k: (v[:, shuf] if k != "mat_klines2sublines" else v) for k, v in sides[0][1].items()}
+    ds = eng.encode(engine.LineBatch.from_images([im]).to(DEV)).cpu().numpy()
+    assert np.abs(ds - d0[L:2 * L][shuf]).max() < 1e-4
+    # side 1 line j is side 0 line perm[j]: a match (i -> j) must satisfy perm[j] == i
+    for p in range(P):
+        m = res.pair(p).cpu().numpy()
+        ok = m >= 0
+        assert ok.sum() >= 0.9 * L
+        assert np.array_equal(perms[p][m[ok]], np.nonzero(ok)[0])
