@@ -102,3 +102,19 @@ def test_shipped_checkpoint():
     assert np.abs(d0 - npz["real_pair_L128_d0"]).max() < TOL
     assert np.abs(d1 - npz["real_pair_L128_d1"]).max() < TOL
     assert np.array_equal(orc.match_indices(mat), npz["real_pair_L128_mat_idx"])
+
+
+def test_torch_timing_port_matches_oracle_and_reference():
+    """oracle/linetr_oracle_torch.py (the CPU baseline that bench.py times) gives the same
+    answers as the numpy oracle and the committed reference outputs."""
+    from oracle import linetr_oracle_torch as port
+    npz, meta = H.golden()
+    for name in ("enc_L16_T21", "enc_L37_T5_ragged", "enc_L9_T21_nd2"):
+        case = meta["cases"][name]
+        got = port.line_transformer_forward(port.prepare(H.weights_for(case["weights"])), H.case_inputs(case)).numpy()
+        assert np.abs(got - npz[name]).max() < TOL
+    case = meta["cases"]["pair_L32_27"]
+    a, b, _ = syn.make_pair_inputs(case["seed"], case["L0"], case["T"], n_lines1=case["L1"],
+                                   n_real_tokens=tuple(case["ntok"]))
+    mat, dk, d0, _ = port.match_pair(port.prepare(H.weights_for(case["weights"])), a, b, case["thr"])
+    assert np.array_equal(mat, npz["pair_L32_27_mat"]) and np.abs(d0 - npz["pair_L32_27_d0"]).max() < TOL
