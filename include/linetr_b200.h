@@ -175,6 +175,13 @@ int ltr_linear(const float* x, int32_t ldx, const float* w, const float* bias, c
                int32_t ldr, float* y, int32_t ldy, int32_t m, int32_t n, int32_t k, int32_t act,
                int32_t device, void* stream);
 
+/* The same on the tensor-core engine (tcgen05, split-bf16 operands).  `w_host` is a HOST
+ * pointer to the fp32 [n, k] weights: it is packed, uploaded, used and freed inside the call
+ * (synchronous; unit-test hook only).  n and k must be multiples of 64. */
+int ltr_linear_tc(const float* x, int32_t ldx, const float* w_host, const float* bias,
+                  const float* res, int32_t ldr, float* y, int32_t ldy, int32_t m, int32_t n,
+                  int32_t k, int32_t act, int32_t device, void* stream);
+
 /* Instrumentation.  Kernel launches issued by this library since the last reset. */
 int64_t ltr_launch_count(void);
 void ltr_reset_launch_count(void);

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "encoder_kernels.cuh"
 #include "linear_f32.cuh"
+#include "linear_tc.cuh"
 #include "match_kernels.cuh"
 
 namespace ltr {
@@ -42,16 +43,24 @@ cudaEvent_t Profiler::get() {
 }
 
 // ------------------------------------------------------------------ packed model
-struct MlpTail {  // the two wide layers of a positional encoder (128->256 relu, 256->256)
+// One wide linear layer: fp32 weights (CUDA-core engine) and the packed split-bf16 image
+// (tensor-core engine) of the same folded matrix.
+struct Lin {
+  const float* w = nullptr;
+  const float* b = nullptr;
+  TcWeight tw;
+};
+
+struct MlpTail {  // positional encoder: narrow head + the two wide layers (128->256 relu, 256->256)
   SmallMlpWeights head;
-  float *w4, *b4, *w5, *b5;
+  Lin l4, l5;
 };
 
 struct SigLayer {
-  float *wqkv, *bqkv;  // [768,256] head-major rows, q rows pre-scaled by 1/8
-  float *wm, *bm;      // [256,256] merge, input columns head-major
-  float *w1, *b1;      // [512,512] BN folded
-  float *w2, *b2;      // [256,512]
+  Lin qkv;    // [768,256] head-major rows, q rows pre-scaled by 1/8
+  Lin merge;  // [256,256] input columns head-major
+  Lin mlp1;   // [512,512] BN folded
+  Lin mlp2;   // [256,512]
 };
 
 }  // namespace ltr
@@ -60,29 +69,57 @@ struct LtrModel {
   int device = 0;
   LtrConfig cfg{};
   float* arena = nullptr;
+  uint16_t* tc_arena = nullptr;
   size_t arena_floats = 0;
   ltr::MlpTail wpe{}, lpe{};
   float *U = nullptr, *s_cls = nullptr, *cls = nullptr;
-  float *wv = nullptr, *bv = nullptr, *wfc = nullptr, *bfc = nullptr, *ln1g = nullptr, *ln1b = nullptr;
-  float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+  ltr::Lin wv, wfc, w1, w2, wf;  // wv: 4 heads of [64,256]; wfc bias includes the CLS residual
+  float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
   std::vector<ltr::SigLayer> sig;
-  float *wf = nullptr, *bf = nullptr;
   int token_chunk = 32768;  // tokens per pass of the token stage (keeps intermediates in L2)
+  bool use_tc = true;       // LINETR_ENGINE=f32 selects the CUDA-core GEMM engine (bring-up / A-B checks)
 };
 
 namespace ltr {
 
 using TensorMap = std::unordered_map<std::string, std::pair<const float*, int64_t>>;
 
+struct LinOff { size_t w, b, tc; int N, K; };
+
 struct HostPack {
   std::vector<float> buf;
+  std::vector<uint16_t> tc;  // packed split-bf16 images: hi at off, lo at off + N*K
   size_t add(const std::vector<double>& v) {
     size_t off = (buf.size() + 63) / 64 * 64;  // 256-byte alignment of every tensor
     buf.resize(off + v.size());
     for (size_t i = 0; i < v.size(); ++i) buf[off + i] = (float)v[i];
     return off;
   }
+  // wide layer [N,K]: fp32 copy + tensor-core image.  `groups` > 1 packs row groups of N/groups
+  // rows as independent matrices (the per-head V projection).
+  LinOff add_lin(const std::vector<double>& W, const std::vector<double>& b, int N, int K, int groups = 1) {
+    LinOff o{add(W), add(b), 0, N, K};
+    size_t off = (tc.size() + 511) / 512 * 512;  // 1024-byte alignment
+    tc.resize(off + 2 * (size_t)N * K);
+    const int gn = N / groups;
+    for (int g = 0; g < groups; ++g)
+      pack_tc_weight(W.data() + (size_t)g * gn * K, gn, K, tc.data() + off + (size_t)g * gn * K,
+                     tc.data() + off + (size_t)N * K + (size_t)g * gn * K);
+    o.tc = off;
+    return o;
+  }
 };
+
+static Lin bind_lin(const LinOff& o, float* fbase, uint16_t* tbase, int groups = 1) {
+  Lin l;
+  l.w = fbase + o.w;
+  l.b = fbase + o.b;
+  l.tw.hi = reinterpret_cast<const __nv_bfloat16*>(tbase + o.tc);
+  l.tw.lo = reinterpret_cast<const __nv_bfloat16*>(tbase + o.tc + (size_t)o.N * o.K);
+  l.tw.N = o.N / groups;
+  l.tw.K = o.K;
+  return l;
+}
 
 static bool fetch(const TensorMap& tm, const std::string& name, int64_t numel, const float** out, std::string& err) {
   auto it = tm.find(name);
@@ -119,7 +156,7 @@ static bool fold_layer(const TensorMap& tm, const std::string& conv, const std::
   return true;
 }
 
-struct MlpOffsets { size_t w[5], b[5]; };
+struct MlpOffsets { size_t w[3], b[3]; LinOff l4, l5; };
 
 static bool pack_pos_encoder(const TensorMap& tm, const std::string& prefix, int in, HostPack& hp, MlpOffsets& off,
                              std::string& err) {
@@ -129,18 +166,24 @@ static bool pack_pos_encoder(const TensorMap& tm, const std::string& prefix, int
     std::string bn = (l < 4) ? prefix + "." + std::to_string(3 * l + 1) : std::string();
     std::vector<double> W, b;
     if (!fold_layer(tm, conv, bn, ch[l + 1], ch[l], W, b, err)) return false;
-    off.w[l] = hp.add(W);
-    off.b[l] = hp.add(b);
+    if (l < 3) {
+      off.w[l] = hp.add(W);
+      off.b[l] = hp.add(b);
+    } else if (l == 3) {
+      off.l4 = hp.add_lin(W, b, ch[l + 1], ch[l]);
+    } else {
+      off.l5 = hp.add_lin(W, b, ch[l + 1], ch[l]);
+    }
   }
   return true;
 }
 
-static void bind_mlp(MlpTail& m, float* base, const MlpOffsets& o) {
+static void bind_mlp(MlpTail& m, float* base, uint16_t* tbase, const MlpOffsets& o) {
   m.head.w1 = base + o.w[0]; m.head.b1 = base + o.b[0];
   m.head.w2 = base + o.w[1]; m.head.b2 = base + o.b[1];
   m.head.w3 = base + o.w[2]; m.head.b3 = base + o.b[2];
-  m.w4 = base + o.w[3]; m.b4 = base + o.b[3];
-  m.w5 = base + o.w[4]; m.b5 = base + o.b[4];
+  m.l4 = bind_lin(o.l4, base, tbase);
+  m.l5 = bind_lin(o.l5, base, tbase);
 }
 
 static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -194,6 +237,22 @@ static LinearArgs lin(const float* A, int lda, const float* W, const float* b, f
   return a;
 }
 
+// Y[M, N] = act(A W^T + b) (+ R) for one wide layer on the selected engine.  nz > 1 runs nz
+// independent [N, K] matrices (A advanced by zA columns, C/bias by N columns per z).
+static int gemm(const LtrModel* m, const Lin& L, const float* A, int lda, float* C, int ldc, int M, int act,
+                cudaStream_t s, const float* R = nullptr, int ldr = 0, int nz = 1, long long zA = 0) {
+  const int N = L.tw.N, K = L.tw.K;
+  if (m->use_tc) {
+    TcArgs a{};
+    a.A = A; a.lda = lda; a.W = L.tw; a.bias = L.b; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc; a.M = M; a.act = act;
+    a.sA = zA; a.sW = (long long)N * K; a.sB = N; a.sR = N; a.sC = N;
+    return launch_linear_tc(a, nz, s);
+  }
+  LinearArgs a = lin(A, lda, L.w, L.b, C, ldc, M, N, K, act, R, ldr);
+  a.nz = nz; a.sA = zA; a.sW = (long long)N * K; a.sB = N; a.sR = N; a.sC = N;
+  return launch_linear_f32(a, s);
+}
+
 template <bool TOKEN>
 static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const float* in1, const float* in2, float* out,
                             int rows, float width, float height, cudaStream_t s) {
@@ -241,10 +300,9 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
     const int64_t t0 = (int64_t)l0 * T;
     LTR_TRY(launch_small_mlp<true>(m->wpe.head, in.pnt + t0 * 2, in.score + t0, nullptr, w.h128, rows, in.image_width,
                                    in.image_height, s));
-    LTR_TRY(launch_linear_f32(lin(w.h128, 128, m->wpe.w4, m->wpe.b4, w.h256, 256, rows, 256, 128, ACT_RELU), s));
+    LTR_TRY(gemm(m, m->wpe.l4, w.h128, 128, w.h256, 256, rows, ACT_RELU, s));
     // x = desc + word_position_enc  (line_transformer.py:117)
-    LTR_TRY(launch_linear_f32(lin(w.h256, 256, m->wpe.w5, m->wpe.b5, w.x, 256, rows, 256, 256, ACT_NONE,
-                                  in.desc + t0 * 256, 256), s));
+    LTR_TRY(gemm(m, m->wpe.l5, w.h256, 256, w.x, 256, rows, ACT_NONE, s, in.desc + t0 * 256, 256));
     {
       LaunchScope ls(KC_CLS_POOL, s);
       cls_pool_kernel<<<nl, CP_THREADS, 0, s>>>(w.x, m->U, m->s_cls, m->cls, w.z + (int64_t)l0 * 1024, T);
@@ -252,20 +310,16 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
     }
   }
   // ---- line stage: V projection per head, fc + CLS residual, LN, FFN, LN, + line pos ----
-  {
-    LinearArgs a = lin(w.z, 1024, m->wv, m->bv, w.ctx, 256, R, 64, 256, ACT_NONE);
-    a.nz = 4; a.sA = 256; a.sW = 64 * 256; a.sB = 64; a.sC = 64;
-    LTR_TRY(launch_linear_f32(a, s));
-  }
-  LTR_TRY(launch_linear_f32(lin(w.ctx, 256, m->wfc, m->bfc, w.y1, 256, R, 256, 256, ACT_NONE), s));
+  LTR_TRY(gemm(m, m->wv, w.z, 1024, w.ctx, 256, R, ACT_NONE, s, nullptr, 0, 4, 256));
+  LTR_TRY(gemm(m, m->wfc, w.ctx, 256, w.y1, 256, R, ACT_NONE, s));
   LTR_TRY(launch_layernorm(w.y1, 256, m->ln1g, m->ln1b, nullptr, 0, w.y1, 256, R, s));
   float* g = w.z;  // z is dead after the V projection
-  LTR_TRY(launch_linear_f32(lin(w.y1, 256, m->w1, m->b1, g, 1024, R, 1024, 256, ACT_GELU), s));
-  LTR_TRY(launch_linear_f32(lin(g, 1024, m->w2, m->b2, w.y2, 256, R, 256, 1024, ACT_NONE, w.y1, 256), s));
+  LTR_TRY(gemm(m, m->w1, w.y1, 256, g, 1024, R, ACT_GELU, s));
+  LTR_TRY(gemm(m, m->w2, g, 1024, w.y2, 256, R, ACT_NONE, s, w.y1, 256));
   LTR_TRY(launch_small_mlp<false>(m->lpe.head, in.sublines, in.resp, in.angle, w.l128, R, in.image_width,
                                   in.image_height, s));
-  LTR_TRY(launch_linear_f32(lin(w.l128, 128, m->lpe.w4, m->lpe.b4, w.l256, 256, R, 256, 128, ACT_RELU), s));
-  LTR_TRY(launch_linear_f32(lin(w.l256, 256, m->lpe.w5, m->lpe.b5, w.lpos, 256, R, 256, 256, ACT_NONE), s));
+  LTR_TRY(gemm(m, m->lpe.l4, w.l128, 128, w.l256, 256, R, ACT_RELU, s));
+  LTR_TRY(gemm(m, m->lpe.l5, w.l256, 256, w.lpos, 256, R, ACT_NONE, s));
   // sentence = klines_pos + LN(ffn)  -> xm[:, :256]
   LTR_TRY(launch_layernorm(w.y2, 256, m->ln2g, m->ln2b, w.lpos, 256, w.xm, 512, R, s));
   // ---- line signature layers ----
@@ -276,18 +330,18 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   }
   for (size_t li = 0; li < m->sig.size(); ++li) {
     const SigLayer& L = m->sig[li];
-    LTR_TRY(launch_linear_f32(lin(w.xm, 512, L.wqkv, L.bqkv, w.qkv, 768, R, 768, 256, ACT_NONE), s));
+    LTR_TRY(gemm(m, L.qkv, w.xm, 512, w.qkv, 768, R, ACT_NONE, s));
     if (max_l > 0) {
       LaunchScope ls(KC_SIG_ATTN, s);
       dim3 grid(cdiv(max_l, SA_THREADS), 4, in.n_images);
       sig_attention_kernel<<<grid, SA_THREADS, 0, s>>>(w.qkv, w.o, 256, cu, in.lines_per_image);
       LTR_CUDA_TRY(cudaGetLastError());
     }
-    LTR_TRY(launch_linear_f32(lin(w.o, 256, L.wm, L.bm, w.xm + 256, 512, R, 256, 256, ACT_NONE), s));
-    LTR_TRY(launch_linear_f32(lin(w.xm, 512, L.w1, L.b1, w.hm, 512, R, 512, 512, ACT_RELU), s));
-    LTR_TRY(launch_linear_f32(lin(w.hm, 512, L.w2, L.b2, w.xm, 512, R, 256, 512, ACT_NONE, w.xm, 512), s));
+    LTR_TRY(gemm(m, L.merge, w.o, 256, w.xm + 256, 512, R, ACT_NONE, s));
+    LTR_TRY(gemm(m, L.mlp1, w.xm, 512, w.hm, 512, R, ACT_RELU, s));
+    LTR_TRY(gemm(m, L.mlp2, w.hm, 512, w.xm, 512, R, ACT_NONE, s, w.xm, 512));
   }
-  LTR_TRY(launch_linear_f32(lin(w.xm, 512, m->wf, m->bf, w.yf, 256, R, 256, 256, ACT_NONE), s));
+  LTR_TRY(gemm(m, m->wf, w.xm, 512, w.yf, 256, R, ACT_NONE, s));
   if (max_l > 0) {
     LaunchScope ls(KC_FINAL_NORM, s);
     dim3 grid(cdiv(max_l, 32), in.n_images);
@@ -415,15 +469,15 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   std::vector<double> bfc_cls(D);
   for (int i = 0; i < D; ++i) bfc_cls[i] = (double)bfc[i] + cls[i];  // fc bias + CLS residual (line_attention.py:72)
   size_t oU = hp.add(U), oS = hp.add(scls), oC = hp.add(vec(cls, D));
-  size_t oWv = hp.add(vec(wv, D * D)), oBv = hp.add(vec(bv, D));
-  size_t oWfc = hp.add(vec(wfc, D * D)), oBfc = hp.add(bfc_cls);
+  LinOff oWv = hp.add_lin(vec(wv, D * D), vec(bv, D), D, D, 4);
+  LinOff oWfc = hp.add_lin(vec(wfc, D * D), bfc_cls, D, D);
   size_t oL1g = hp.add(vec(ln1g, D)), oL1b = hp.add(vec(ln1b, D));
-  size_t oW1 = hp.add(vec(w1, (size_t)DI * D)), oB1 = hp.add(vec(b1, DI));
-  size_t oW2 = hp.add(vec(w2, (size_t)D * DI)), oB2 = hp.add(vec(b2, D));
+  LinOff oW1 = hp.add_lin(vec(w1, (size_t)DI * D), vec(b1, DI), DI, D);
+  LinOff oW2 = hp.add_lin(vec(w2, (size_t)D * DI), vec(b2, D), D, DI);
   size_t oL2g = hp.add(vec(ln2g, D)), oL2b = hp.add(vec(ln2b, D));
 
   // ---- signature layers ----
-  struct SigOff { size_t wqkv, bqkv, wm, bm, w1, b1, w2, b2; };
+  struct SigOff { LinOff qkv, merge, mlp1, mlp2; };
   std::vector<SigOff> so(cfg->n_sig_layers);
   for (int li = 0; li < cfg->n_sig_layers; ++li) {
     const std::string p = "selfattn.layers." + std::to_string(li);
@@ -452,11 +506,12 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
     if (!fold_layer(tm, p + ".mlp.0", p + ".mlp.1", 2 * D, 2 * D, W1, B1, err) ||
         !fold_layer(tm, p + ".mlp.3", "", D, 2 * D, W2, B2, err))
       return set_error(LTR_E_INVALID, err);
-    so[li] = {hp.add(Wqkv), hp.add(bqkv), hp.add(Wm), hp.add(vec(bm, D)), hp.add(W1), hp.add(B1), hp.add(W2), hp.add(B2)};
+    so[li] = {hp.add_lin(Wqkv, bqkv, 768, D), hp.add_lin(Wm, vec(bm, D), D, D), hp.add_lin(W1, B1, 2 * D, 2 * D),
+              hp.add_lin(W2, B2, D, 2 * D)};
   }
   std::vector<double> Wf, Bf;
   if (!fold_layer(tm, "final_proj", "", D, D, Wf, Bf, err)) return set_error(LTR_E_INVALID, err);
-  size_t oWf = hp.add(Wf), oBf = hp.add(Bf);
+  LinOff oWf = hp.add_lin(Wf, Bf, D, D);
 
   LtrModel* m = new LtrModel();
   m->device = device;
@@ -464,21 +519,29 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   m->arena_floats = hp.buf.size();
   cudaError_t ce = cudaMalloc(&m->arena, hp.buf.size() * sizeof(float));
   if (ce == cudaSuccess) ce = cudaMemcpy(m->arena, hp.buf.data(), hp.buf.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMalloc(&m->tc_arena, hp.tc.size() * sizeof(uint16_t));
+  if (ce == cudaSuccess) ce = cudaMemcpy(m->tc_arena, hp.tc.data(), hp.tc.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) {
     if (m->arena) cudaFree(m->arena);
+    if (m->tc_arena) cudaFree(m->tc_arena);
     delete m;
     return set_error(LTR_E_CUDA, std::string("ltr_create: ") + cudaGetErrorString(ce));
   }
   float* B = m->arena;
-  bind_mlp(m->wpe, B, wpe_o);
-  bind_mlp(m->lpe, B, lpe_o);
+  uint16_t* TB = m->tc_arena;
+  bind_mlp(m->wpe, B, TB, wpe_o);
+  bind_mlp(m->lpe, B, TB, lpe_o);
   m->U = B + oU; m->s_cls = B + oS; m->cls = B + oC;
-  m->wv = B + oWv; m->bv = B + oBv; m->wfc = B + oWfc; m->bfc = B + oBfc;
+  m->wv = bind_lin(oWv, B, TB, 4);
+  m->wfc = bind_lin(oWfc, B, TB);
   m->ln1g = B + oL1g; m->ln1b = B + oL1b;
-  m->w1 = B + oW1; m->b1 = B + oB1; m->w2 = B + oW2; m->b2 = B + oB2;
+  m->w1 = bind_lin(oW1, B, TB);
+  m->w2 = bind_lin(oW2, B, TB);
   m->ln2g = B + oL2g; m->ln2b = B + oL2b;
-  for (auto& o : so) m->sig.push_back({B + o.wqkv, B + o.bqkv, B + o.wm, B + o.bm, B + o.w1, B + o.b1, B + o.w2, B + o.b2});
-  m->wf = B + oWf; m->bf = B + oBf;
+  for (auto& o : so)
+    m->sig.push_back({bind_lin(o.qkv, B, TB), bind_lin(o.merge, B, TB), bind_lin(o.mlp1, B, TB), bind_lin(o.mlp2, B, TB)});
+  m->wf = bind_lin(oWf, B, TB);
+  if (const char* e = std::getenv("LINETR_ENGINE")) m->use_tc = std::string(e) != "f32";
   if (const char* e = std::getenv("LINETR_TOKEN_CHUNK")) {
     int v = std::atoi(e);
     if (v > 0) m->token_chunk = v;
@@ -491,6 +554,7 @@ void ltr_destroy(LtrModel* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   if (m->arena) cudaFree(m->arena);
+  if (m->tc_arena) cudaFree(m->tc_arena);
   delete m;
 }
 
@@ -600,6 +664,34 @@ int ltr_linear(const float* x, int32_t ldx, const float* w, const float* bias, c
   if (!x || !w || !y) return set_error(LTR_E_INVALID, "ltr_linear: null argument");
   LTR_CUDA_TRY(cudaSetDevice(device));
   return launch_linear_f32(lin(x, ldx, w, bias, y, ldy, m, n, k, act, res, ldr), as_stream(stream));
+}
+
+int ltr_linear_tc(const float* x, int32_t ldx, const float* w_host, const float* bias, const float* res, int32_t ldr,
+                  float* y, int32_t ldy, int32_t m, int32_t n, int32_t k, int32_t act, int32_t device, void* stream) {
+  if (!x || !w_host || !y) return set_error(LTR_E_INVALID, "ltr_linear_tc: null argument");
+  if (n % 64 || k % 64) return set_error(LTR_E_UNSUPPORTED, "ltr_linear_tc: n and k must be multiples of 64");
+  LTR_CUDA_TRY(cudaSetDevice(device));
+  std::vector<double> W((size_t)n * k);
+  for (size_t i = 0; i < W.size(); ++i) W[i] = w_host[i];
+  std::vector<uint16_t> img(2 * (size_t)n * k);
+  pack_tc_weight(W.data(), n, k, img.data(), img.data() + (size_t)n * k);
+  uint16_t* d = nullptr;
+  LTR_CUDA_TRY(cudaMalloc(&d, img.size() * sizeof(uint16_t)));
+  cudaError_t ce = cudaMemcpy(d, img.data(), img.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+  int rc = 0;
+  if (ce == cudaSuccess) {
+    TcArgs a{};
+    a.A = x; a.lda = ldx; a.bias = bias; a.R = res; a.ldr = ldr; a.C = y; a.ldc = ldy; a.M = m; a.act = act;
+    a.W.hi = reinterpret_cast<const __nv_bfloat16*>(d);
+    a.W.lo = reinterpret_cast<const __nv_bfloat16*>(d + (size_t)n * k);
+    a.W.N = n; a.W.K = k;
+    rc = launch_linear_tc(a, 1, as_stream(stream));
+    ce = cudaStreamSynchronize(as_stream(stream));
+  }
+  cudaFree(d);
+  if (rc != 0) return rc;
+  if (ce != cudaSuccess) return set_error(LTR_E_CUDA, std::string("ltr_linear_tc: ") + cudaGetErrorString(ce));
+  return LTR_OK;
 }
 
 }  // extern "C"

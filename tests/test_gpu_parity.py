@@ -61,6 +61,24 @@ def test_linear_engine_vs_torch_fp32(M, N_, K, act):
     assert (got - want).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("M,N_,K,act", [(1, 64, 64, 0), (128, 64, 64, 0), (127, 256, 128, 1), (300, 768, 256, 0),
+                                        (513, 1024, 256, 2), (64, 256, 1024, 0), (2816, 256, 256, 0),
+                                        (130, 512, 512, 1), (200, 128, 256, 0)])
+def test_linear_tensor_core_engine_vs_fp64(M, N_, K, act):
+    """tcgen05 engine with split-bf16 operands (hi*hi + lo*hi + hi*lo) against an fp64 reference:
+    ~1e-5 relative, far inside the 1e-3 descriptor budget (plain bf16 would be ~1e-2)."""
+    g = torch.Generator().manual_seed(M * 7 + K + N_)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N_, K, generator=g) / K ** 0.5
+    b = torch.randn(N_, generator=g)
+    r = torch.randn(M, N_, generator=g)
+    want = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    want = [want, torch.relu(want), torch.nn.functional.gelu(want)][act] + r.double()
+    got = _ops.linear(x.to(DEV), w, b.to(DEV), r.to(DEV), act, engine="tc").cpu().double()
+    err = (got - want).abs().max().item()
+    assert err < 1e-4, err
+
+
 # ------------------------------------------------------------------ encoder
 @pytest.mark.parametrize("name", H.ENC_CASES)
 def test_forward_vs_reference_golden_and_oracle(name):
