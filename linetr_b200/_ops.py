@@ -211,3 +211,21 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias=None, res=None, act=0, engine=
                 x.device.index, _stream_ptr(x.device))
     N.check(rc, "ltr_linear")
     return y
+
+
+def linear_img(x: torch.Tensor, w: torch.Tensor, bias=None, res=None, act=0, bn_hint=0):
+    """ltr_linear_img (unit-test hook of the image-operand GEMM engine): returns (y_fp32, y_from_image)."""
+    _req_cuda(x, "x")
+    x = _f32c(x)
+    w = _f32c(w).cpu()
+    M, K = x.shape
+    Nn = w.shape[0]
+    y = torch.empty((M, Nn), dtype=torch.float32, device=x.device)
+    y2 = torch.empty((M, Nn), dtype=torch.float32, device=x.device)
+    bias = _f32c(bias) if bias is not None else None
+    res = _f32c(res) if res is not None else None
+    with torch.cuda.device(x.device):
+        rc = N.load().ltr_linear_img(_ptr(x), K, _ptr(w), _ptr(bias), _ptr(res), Nn, _ptr(y), Nn, _ptr(y2), M, Nn, K,
+                                     int(act), int(bn_hint), x.device.index, _stream_ptr(x.device))
+    N.check(rc, "ltr_linear_img")
+    return y, y2

@@ -85,7 +85,7 @@ __device__ __forceinline__ void image_range(const int* __restrict__ cu, int lpi,
   if (cu) { b = cu[i]; e = cu[i + 1]; } else { b = i * lpi; e = b + lpi; }
 }
 
-static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace ltr

@@ -2,6 +2,7 @@
 // narrow positional-encoder layers, folded CLS attention pooling, LayerNorm,
 // line-signature attention, final L2 normalisation.
 #pragma once
+#include "act_img.cuh"
 #include "common.cuh"
 
 namespace ltr {
@@ -40,7 +41,7 @@ struct SmallMlpSmem {
 template <bool TOKEN>
 __global__ void __launch_bounds__(SM_WARPS * 32)
 small_mlp_kernel(SmallMlpWeights w, const float* __restrict__ in0, const float* __restrict__ in1,
-                 const float* __restrict__ in2, float* __restrict__ out, int rows, float cx, float cy,
+                 const float* __restrict__ in2, ActImg out, int rows, float cx, float cy,
                  float scale) {
   constexpr int IN = TOKEN ? 3 : 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,7 +145,7 @@ small_mlp_kernel(SmallMlpWeights w, const float* __restrict__ in0, const float* 
         int row = r0 + r;
         if (row < rows) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) out[(long long)row * 128 + lane + 32 * j] = fmaxf(acc[j][r], 0.f);
+          for (int j = 0; j < 4; ++j) img_store1(out, row, lane + 32 * j, fmaxf(acc[j][r], 0.f));
         }
       }
     }
@@ -159,14 +160,14 @@ small_mlp_kernel(SmallMlpWeights w, const float* __restrict__ in0, const float* 
 // u_h = W_k,h^T q_h / 8; the constant cancels in the softmax.  Output per line and head:
 // z_h = sum_n softmax_n(s_h)[n] * x[n]   (n = 0 is the CLS token itself), which the caller
 // multiplies by W_v,h (sum of probabilities is 1, so the V bias passes through).
-// x: [lines*T, 256] (= desc + word positional encoding); z: [lines, 4*256].
+// x: [lines*T, 256] (= desc + word positional encoding); z: image of [lines, 4*256] (row line0 + blockIdx.x).
 constexpr int CP_THREADS = 256;
 constexpr int CP_MAXN = 129;  // T <= 128
 
 __global__ void __launch_bounds__(CP_THREADS)
 cls_pool_kernel(const float* __restrict__ x, const float* __restrict__ U /*[4][256]*/,
                 const float* __restrict__ s_cls /*[4]*/, const float* __restrict__ cls /*[256]*/,
-                float* __restrict__ z, int T) {
+                ActImg z, int line0, int T) {
   __shared__ float sc[CP_MAXN][4];
   const int line = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* __restrict__ xl = x + (long long)line * T * 256;
@@ -218,8 +219,11 @@ cls_pool_kernel(const float* __restrict__ x, const float* __restrict__ U /*[4][2
     z2 = fmaf(sc[n + 1][2], xv, z2);
     z3 = fmaf(sc[n + 1][3], xv, z3);
   }
-  float* zl = z + (long long)line * 1024;
-  zl[c] = z0; zl[256 + c] = z1; zl[512 + c] = z2; zl[768 + c] = z3;
+  const int zr = line0 + line;
+  img_store1(z, zr, c, z0);
+  img_store1(z, zr, 256 + c, z1);
+  img_store1(z, zr, 512 + c, z2);
+  img_store1(z, zr, 768 + c, z3);
 }
 
 // ------------------------------------------------------------------------------------
@@ -230,7 +234,7 @@ cls_pool_kernel(const float* __restrict__ x, const float* __restrict__ U /*[4][2
 __global__ void __launch_bounds__(256)
 layernorm256_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ add, int lda,
-                    float* __restrict__ out, int ldo, int rows, float eps) {
+                    float* __restrict__ out, int ldo, ActImg oimg, int o_k0, int rows, float eps) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* p = in + (long long)row * ldi;
@@ -253,9 +257,15 @@ layernorm256_kernel(const float* __restrict__ in, int ldi, const float* __restri
     o0.x += c0.x; o0.y += c0.y; o0.z += c0.z; o0.w += c0.w;
     o1.x += c1.x; o1.y += c1.y; o1.z += c1.z; o1.w += c1.w;
   }
-  float* o = out + (long long)row * ldo;
-  *reinterpret_cast<float4*>(o + lane * 4) = o0;
-  *reinterpret_cast<float4*>(o + 128 + lane * 4) = o1;
+  if (out) {
+    float* o = out + (long long)row * ldo;
+    *reinterpret_cast<float4*>(o + lane * 4) = o0;
+    *reinterpret_cast<float4*>(o + 128 + lane * 4) = o1;
+  }
+  if (oimg.hi) {
+    img_store4(oimg, row, o_k0 + lane * 4, o0.x, o0.y, o0.z, o0.w);
+    img_store4(oimg, row, o_k0 + 128 + lane * 4, o1.x, o1.y, o1.z, o1.w);
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -264,12 +274,11 @@ layernorm256_kernel(const float* __restrict__ in, int ldi, const float* __restri
 // qkv: [n_lines, 768] = [q | k | v], each head-major (c = h*64 + d; the reference's
 // interleaved c = d*4 + h layout is undone when the weights are packed, and 1/8 is folded
 // into W_q).  One thread per query row, keys/values staged through shared memory in
-// tiles of 64, online softmax in chunks of 16 keys.  out: [n_lines, ldo] head-major.
+// tiles of 64, online softmax in chunks of 16 keys.  out: image of [n_lines, 256] head-major.
 constexpr int SA_THREADS = 128, SA_KT = 64, SA_CH = 16;
 
 __global__ void __launch_bounds__(SA_THREADS)
-sig_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int ldo,
-                     const int* __restrict__ cu, int lpi) {
+sig_attention_kernel(const float* __restrict__ qkv, ActImg out, const int* __restrict__ cu, int lpi) {
   __shared__ __align__(16) float Ks[SA_KT][64];
   __shared__ __align__(16) float Vs[SA_KT][64];
   int lb, le;
@@ -345,10 +354,12 @@ sig_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   }
   if (active) {
     float inv = 1.f / l;
-    float* op = out + (long long)(lb + qi) * ldo + h * 64;
 #pragma unroll
-    for (int d = 0; d < 64; d += 4)
-      *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+    for (int d = 0; d < 64; d += 8) {
+      const float v[8] = {o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv,
+                          o[d + 4] * inv, o[d + 5] * inv, o[d + 6] * inv, o[d + 7] * inv};
+      img_store8(out, lb + qi, h * 64 + d, v);
+    }
   }
 }
 

@@ -1,0 +1,280 @@
+// Persistent tensor-core GEMM for sm_100a whose operands travel as split-bf16 "tile images".
+//
+//   Y = act(X W^T + b) (+ R),   X given as an activation image, Y written as fp32 rows and/or
+//   as the activation image the next layer consumes.
+//
+// Activation image (ActImg) of a row-major activation [M, K]: two planes (bf16 hi, bf16 lo with
+// x ~= hi + lo), each a sequence of 16 KB tiles [m_tile = row/128][k_block = k/64] holding
+// 128 rows x 64 k in the K-major SWIZZLE_128B layout tcgen05 reads.  A tile is therefore ONE
+// contiguous cp.async.bulk (TMA) transfer and needs no CUDA-core work on the consumer side.
+// Weights use the same trick (TcWeight, linear_tc.cuh).
+//
+// The main loop is pure TMA + tcgen05:  warp 0 streams A and W tiles through an mbarrier
+// ring, warp 1 issues 3 MMAs per k-step (lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM),
+// warps 2-9 drain finished accumulators (tcgen05.ld), apply bias / activation / residual and
+// write fp32 rows and/or the split-bf16 image of the result.  TMEM holds two accumulators so
+// the epilogue of tile i overlaps the MMAs of tile i+1; CTAs are persistent (one per SM) and
+// walk the tile list round-robin.
+#pragma once
+#include "common.cuh"
+#include "linear_f32.cuh"
+#include "linear_tc.cuh"
+#include "act_img.cuh"
+#include "ptx_sm100.cuh"
+
+namespace ltr {
+
+struct GemmImgArgs {
+  ActImg A; int a_kb0;       // contract k-blocks [a_kb0, a_kb0 + W.K/64) of A
+  TcWeight W;
+  const float* bias;
+  const float* R; int ldr;   // fp32 residual (added after the activation) or nullptr
+  float* C; int ldc;         // fp32 output or nullptr
+  ActImg O; int o_kb0;       // image output (O.hi == nullptr: none); column n -> k-block o_kb0 + n/64
+  int M, act;
+  int m_tiles, n_blks;
+};
+
+template <int BN>
+struct GemmImgCfg {
+  static constexpr int A_TILE = 16384;            // one plane of a 128x64 bf16 tile
+  static constexpr int W_TILE = BN * 128;         // one plane of a BN x 64 bf16 tile
+  static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
+  static constexpr int STAGES = BN >= 256 ? 2 : 3;
+  static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;        // two accumulators
+  static constexpr int THREADS = 320;             // TMA warp, MMA warp, 8 epilogue warps
+};
+
+template <int BN>
+__global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
+  using Cfg = GemmImgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk = p.W.K / 64;
+  const int n_tiles = p.m_tiles * p.n_blks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&acc_full[b], 1);
+      ptx::mbar_init(&acc_empty[b], 8);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      const uint8_t* whi = reinterpret_cast<const uint8_t*>(p.W.hi);
+      const uint8_t* wlo = reinterpret_cast<const uint8_t*>(p.W.lo);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_blks, nb = tile - mt * p.n_blks;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          const uint32_t ph = (it / Cfg::STAGES) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * Cfg::STAGE;
+          const size_t aoff = ((size_t)mt * p.A.kblocks + p.a_kb0 + kb) * IMG_TILE_ELEMS;
+          const size_t woff = ((size_t)kb * (p.W.N / 8) + (size_t)nb * (BN / 8)) * 1024;
+          ptx::mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
+          ptx::bulk_g2s(st, p.A.hi + aoff, Cfg::A_TILE, &full[s]);
+          ptx::bulk_g2s(st + Cfg::A_TILE, p.A.lo + aoff, Cfg::A_TILE, &full[s]);
+          ptx::bulk_g2s(st + 2 * Cfg::A_TILE, whi + woff, Cfg::W_TILE, &full[s]);
+          ptx::bulk_g2s(st + 2 * Cfg::A_TILE + Cfg::W_TILE, wlo + woff, Cfg::W_TILE, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+        ptx::mbar_wait(&acc_empty[buf], aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          const uint32_t ph = (it / Cfg::STAGES) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(smem + s * Cfg::STAGE);
+          const uint32_t a_lo = a_hi + Cfg::A_TILE;
+          const uint32_t w_hi = a_hi + 2 * Cfg::A_TILE;
+          const uint32_t w_lo = w_hi + Cfg::W_TILE;
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint32_t ko = k16 * 32;
+            const uint64_t dah = ptx::make_sw128_kmajor_desc(a_hi + ko, 1024);
+            const uint64_t dal = ptx::make_sw128_kmajor_desc(a_lo + ko, 1024);
+            const uint64_t dwh = ptx::make_sw128_kmajor_desc(w_hi + ko, 1024);
+            const uint64_t dwl = ptx::make_sw128_kmajor_desc(w_lo + ko, 1024);
+            ptx::umma_bf16(d_tmem, dal, dwh, idesc, (kb | k16) != 0);
+            ptx::umma_bf16(d_tmem, dah, dwl, idesc, 1);
+            ptx::umma_bf16(d_tmem, dah, dwh, idesc, 1);
+          }
+          ptx::umma_commit(&empty[s]);
+        }
+        ptx::umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (8 warps)
+    const int q = warp & 3;           // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;  // which half of the BN columns
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int mt = tile / p.n_blks, nb = tile - mt * p.n_blks;
+      const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+      ptx::mbar_wait(&acc_full[buf], aph);
+      ptx::tc_fence_after();
+      const int r_in = q * 32 + lane;
+      const int row = mt * 128 + r_in;
+      const bool live = row < p.M;
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        float acc[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c0, acc);
+        if (live) {
+          const int nbase = nb * BN + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = nbase + j;
+            const float4 b = p.bias ? *reinterpret_cast<const float4*>(p.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[j] = apply_act(acc[j] + b.x, p.act);
+            acc[j + 1] = apply_act(acc[j + 1] + b.y, p.act);
+            acc[j + 2] = apply_act(acc[j + 2] + b.z, p.act);
+            acc[j + 3] = apply_act(acc[j + 3] + b.w, p.act);
+            if (p.R) {
+              const float4 rr = *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + n);
+              acc[j] += rr.x; acc[j + 1] += rr.y; acc[j + 2] += rr.z; acc[j + 3] += rr.w;
+            }
+            if (p.C) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + n) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          }
+          if (p.O.hi) {
+            const int kb_out = p.o_kb0 + (nbase >> 6);
+            const size_t toff = ((size_t)mt * p.O.kblocks + kb_out) * IMG_TILE_ELEMS;
+            uint8_t* ohi = reinterpret_cast<uint8_t*>(p.O.hi + toff);
+            uint8_t* olo = reinterpret_cast<uint8_t*>(p.O.lo + toff);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __nv_bfloat16 h[8], l[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) ptx::split_bf16(acc[j + e], h[e], l[e]);
+              const uint32_t off = ptx::sw128_offset(r_in, (nbase & 63) + j);
+              *reinterpret_cast<uint4*>(ohi + off) =
+                  make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
+              *reinterpret_cast<uint4*>(olo + off) =
+                  make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+inline int device_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <int BN>
+static int launch_gemm_img_bn(GemmImgArgs a, cudaStream_t s) {
+  using Cfg = GemmImgCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LTR_CUDA_TRY(cudaFuncSetAttribute(gemm_img_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  a.m_tiles = cdiv(a.M, 128);
+  a.n_blks = a.W.N / BN;
+  const int tiles = a.m_tiles * a.n_blks;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  LaunchScope ls(KC_LINEAR, s);
+  gemm_img_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(a);
+  LTR_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// bn_hint: 0 = choose (256 when N % 256 == 0 and that still gives >= 1 tile per SM, else 128)
+inline int launch_gemm_img(const GemmImgArgs& a, cudaStream_t s, int bn_hint = 0) {
+  if (a.M <= 0) return 0;
+  if (a.W.K % 64 || a.W.N % 128 || (a.C && a.ldc % 4) || (a.R && a.ldr % 4))
+    return set_error(-1, "gemm_img: K%64, N%128, ld%4 required");
+  int bn = bn_hint;
+  if (!bn) {
+    bn = 128;
+    if (a.W.N % 256 == 0 && (long long)cdiv(a.M, 128) * (a.W.N / 256) >= device_sm_count()) bn = 256;
+  }
+  if (bn == 256 && a.W.N % 256 == 0) return launch_gemm_img_bn<256>(a, s);
+  return launch_gemm_img_bn<128>(a, s);
+}
+
+// ---------------------------------------------------------------- image <-> fp32 helpers
+// fp32 rows [M, K] (ld) -> image k-blocks [kb0, kb0 + K/64); one thread per 8 consecutive k.
+__global__ void __launch_bounds__(256) to_image_kernel(const float* __restrict__ x, int ld, int M, int K, ActImg o, int kb0) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int k8 = K / 8;
+  if (idx >= (long long)M * k8) return;
+  const int row = (int)(idx / k8), k = (int)(idx % k8) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(x + (long long)row * ld + k);
+  const float4 b = *reinterpret_cast<const float4*>(x + (long long)row * ld + k + 4);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ptx::split_bf16(v[e], h[e], l[e]);
+  const size_t toff = ((size_t)(row >> 7) * o.kblocks + kb0 + (k >> 6)) * IMG_TILE_ELEMS;
+  const uint32_t off = ptx::sw128_offset(row & 127, k & 63);
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o.hi + toff) + off) =
+      make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o.lo + toff) + off) =
+      make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+}
+
+// image k-blocks [kb0, kb0 + K/64) -> fp32 rows (hi + lo); test helper.
+__global__ void __launch_bounds__(256) from_image_kernel(ActImg a, int kb0, float* __restrict__ y, int ld, int M, int K) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)M * K) return;
+  const int row = (int)(idx / K), k = (int)(idx % K);
+  const size_t toff = ((size_t)(row >> 7) * a.kblocks + kb0 + (k >> 6)) * IMG_TILE_ELEMS;
+  const uint32_t off = ptx::sw128_offset(row & 127, k & 63) / 2;
+  y[(long long)row * ld + k] = __bfloat162float(a.hi[toff + off]) + __bfloat162float(a.lo[toff + off]);
+}
+
+}  // namespace ltr

@@ -11,6 +11,7 @@
 #include "encoder_kernels.cuh"
 #include "linear_f32.cuh"
 #include "linear_tc.cuh"
+#include "gemm_img.cuh"
 #include "match_kernels.cuh"
 
 namespace ltr {
@@ -77,7 +78,6 @@ struct LtrModel {
   float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
   std::vector<ltr::SigLayer> sig;
   int token_chunk = 32768;  // tokens per pass of the token stage (keeps intermediates in L2)
-  bool use_tc = true;       // LINETR_ENGINE=f32 selects the CUDA-core GEMM engine (bring-up / A-B checks)
 };
 
 namespace ltr {
@@ -190,9 +190,15 @@ static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 // ------------------------------------------------------------------ workspace
 struct EncodeWs {
-  float *h128, *h256, *x;                       // token stage, one chunk
-  float *z, *ctx, *y1, *y2, *l128, *l256, *lpos;  // line stage ([R, *])
-  float *xm, *qkv, *o, *hm, *yf;                // signature stage
+  // token stage, one chunk of lines (kept L2 resident)
+  ActImg h128, h256;   // images [chunk tokens, 128 / 256]
+  float* x;            // fp32 [chunk tokens, 256] = desc + word positional encoding
+  // line stage
+  ActImg z, ctx, y1i, g, l128, l256;  // images [R, 1024 / 256 / 256 / 1024 / 128 / 256]
+  float *y1pre, *y1, *y2pre, *lpos;   // fp32 [R, 256]
+  // signature stage
+  ActImg xm, o, hm;    // images [R, 512] = [x | message], [R, 256], [R, 512]
+  float *xf, *qkv, *yf;  // fp32 [R, 256] running descriptor, [R, 768], [R, 256]
   int chunk_lines;
   int64_t bytes;
 };
@@ -200,31 +206,44 @@ struct EncodeWs {
 static EncodeWs carve(const LtrModel* m, int n_lines, int T, char* base) {
   EncodeWs w{};
   int64_t off = 0;
-  auto take = [&](int64_t floats) {
-    float* p = reinterpret_cast<float*>(base + off);
-    off = align_up(off + floats * 4, 256);
+  auto take = [&](int64_t bytes) {
+    char* p = base + off;
+    off = align_up(off + bytes, 1024);
     return p;
+  };
+  auto takef = [&](int64_t floats) { return reinterpret_cast<float*>(take(floats * 4)); };
+  auto takei = [&](int64_t rows, int K) {
+    const int64_t mpad = align_up(rows, 128);
+    ActImg a;
+    a.hi = reinterpret_cast<__nv_bfloat16*>(take(mpad * K * 2));
+    a.lo = reinterpret_cast<__nv_bfloat16*>(take(mpad * K * 2));
+    a.kblocks = K / 64;
+    return a;
   };
   int cl = m->token_chunk / T;
   if (cl < 1) cl = 1;
   if (cl > n_lines) cl = n_lines > 0 ? n_lines : 1;
   w.chunk_lines = cl;
   const int64_t ct = (int64_t)cl * T, R = n_lines;
-  w.h128 = take(ct * 128);
-  w.h256 = take(ct * 256);
-  w.x = take(ct * 256);
-  w.z = take(R * 1024);  // also the FFN hidden buffer
-  w.ctx = take(R * 256);
-  w.y1 = take(R * 256);
-  w.y2 = take(R * 256);
-  w.l128 = take(R * 128);
-  w.l256 = take(R * 256);
-  w.lpos = take(R * 256);
-  w.xm = take(R * 512);
-  w.qkv = take(R * 768);
-  w.o = take(R * 256);
-  w.hm = take(R * 512);
-  w.yf = take(R * 256);
+  w.h128 = takei(ct, 128);
+  w.h256 = takei(ct, 256);
+  w.x = takef(ct * 256);
+  w.z = takei(R, 1024);
+  w.ctx = takei(R, 256);
+  w.y1i = takei(R, 256);
+  w.g = takei(R, 1024);
+  w.l128 = takei(R, 128);
+  w.l256 = takei(R, 256);
+  w.y1pre = takef(R * 256);
+  w.y1 = takef(R * 256);
+  w.y2pre = takef(R * 256);
+  w.lpos = takef(R * 256);
+  w.xm = takei(R, 512);
+  w.o = takei(R, 256);
+  w.hm = takei(R, 512);
+  w.xf = takef(R * 256);
+  w.qkv = takef(R * 768);
+  w.yf = takef(R * 256);
   w.bytes = off;
   return w;
 }
@@ -237,24 +256,19 @@ static LinearArgs lin(const float* A, int lda, const float* W, const float* b, f
   return a;
 }
 
-// Y[M, N] = act(A W^T + b) (+ R) for one wide layer on the selected engine.  nz > 1 runs nz
-// independent [N, K] matrices (A advanced by zA columns, C/bias by N columns per z).
-static int gemm(const LtrModel* m, const Lin& L, const float* A, int lda, float* C, int ldc, int M, int act,
-                cudaStream_t s, const float* R = nullptr, int ldr = 0, int nz = 1, long long zA = 0) {
-  const int N = L.tw.N, K = L.tw.K;
-  if (m->use_tc) {
-    TcArgs a{};
-    a.A = A; a.lda = lda; a.W = L.tw; a.bias = L.b; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc; a.M = M; a.act = act;
-    a.sA = zA; a.sW = (long long)N * K; a.sB = N; a.sR = N; a.sC = N;
-    return launch_linear_tc(a, nz, s);
-  }
-  LinearArgs a = lin(A, lda, L.w, L.b, C, ldc, M, N, K, act, R, ldr);
-  a.nz = nz; a.sA = zA; a.sW = (long long)N * K; a.sB = N; a.sR = N; a.sC = N;
-  return launch_linear_f32(a, s);
+// One wide layer on the tensor-core engine: A image k-blocks [a_kb0, a_kb0 + K/64) -> fp32 rows C
+// (optional) and/or image O k-blocks from o_kb0 (optional); R = fp32 residual.
+static int gemm(const Lin& L, const ActImg& A, int a_kb0, int M, int act, cudaStream_t s, float* C, int ldc,
+                const ActImg* O = nullptr, int o_kb0 = 0, const float* R = nullptr, int ldr = 0) {
+  GemmImgArgs a{};
+  a.A = A; a.a_kb0 = a_kb0; a.W = L.tw; a.bias = L.b; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc;
+  if (O) { a.O = *O; a.o_kb0 = o_kb0; }
+  a.M = M; a.act = act;
+  return launch_gemm_img(a, s);
 }
 
 template <bool TOKEN>
-static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const float* in1, const float* in2, float* out,
+static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const float* in1, const float* in2, ActImg out,
                             int rows, float width, float height, cudaStream_t s) {
   if (rows <= 0) return 0;
   constexpr int IN = TOKEN ? 3 : 5;
@@ -275,10 +289,10 @@ static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const fl
 }
 
 static int launch_layernorm(const float* in, int ldi, const float* g, const float* b, const float* add, int lda,
-                            float* out, int ldo, int rows, cudaStream_t s) {
+                            float* out, int ldo, ActImg oimg, int o_k0, int rows, cudaStream_t s) {
   if (rows <= 0) return 0;
   LaunchScope ls(KC_LAYERNORM, s);
-  layernorm256_kernel<<<cdiv(rows, 8), 256, 0, s>>>(in, ldi, g, b, add, lda, out, ldo, rows, 1e-6f);
+  layernorm256_kernel<<<cdiv(rows, 8), 256, 0, s>>>(in, ldi, g, b, add, lda, out, ldo, oimg, o_k0, rows, 1e-6f);
   LTR_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -293,35 +307,34 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
                        cudaStream_t s) {
   const int R = in.n_lines, T = in.n_tokens;
   const int* cu = in.cu_lines_dev;
-  // ---- token stage, chunked over lines so that h128/h256/x stay L2 resident ----
+  // ---- token stage, chunked over lines so that the intermediates stay L2 resident ----
   for (int l0 = 0; l0 < R; l0 += w.chunk_lines) {
     const int nl = std::min(w.chunk_lines, R - l0);
     const int rows = nl * T;
     const int64_t t0 = (int64_t)l0 * T;
     LTR_TRY(launch_small_mlp<true>(m->wpe.head, in.pnt + t0 * 2, in.score + t0, nullptr, w.h128, rows, in.image_width,
                                    in.image_height, s));
-    LTR_TRY(gemm(m, m->wpe.l4, w.h128, 128, w.h256, 256, rows, ACT_RELU, s));
+    LTR_TRY(gemm(m->wpe.l4, w.h128, 0, rows, ACT_RELU, s, nullptr, 0, &w.h256, 0));
     // x = desc + word_position_enc  (line_transformer.py:117)
-    LTR_TRY(gemm(m, m->wpe.l5, w.h256, 256, w.x, 256, rows, ACT_NONE, s, in.desc + t0 * 256, 256));
+    LTR_TRY(gemm(m->wpe.l5, w.h256, 0, rows, ACT_NONE, s, w.x, 256, nullptr, 0, in.desc + t0 * 256, 256));
     {
       LaunchScope ls(KC_CLS_POOL, s);
-      cls_pool_kernel<<<nl, CP_THREADS, 0, s>>>(w.x, m->U, m->s_cls, m->cls, w.z + (int64_t)l0 * 1024, T);
+      cls_pool_kernel<<<nl, CP_THREADS, 0, s>>>(w.x, m->U, m->s_cls, m->cls, w.z, l0, T);
       LTR_CUDA_TRY(cudaGetLastError());
     }
   }
-  // ---- line stage: V projection per head, fc + CLS residual, LN, FFN, LN, + line pos ----
-  LTR_TRY(gemm(m, m->wv, w.z, 1024, w.ctx, 256, R, ACT_NONE, s, nullptr, 0, 4, 256));
-  LTR_TRY(gemm(m, m->wfc, w.ctx, 256, w.y1, 256, R, ACT_NONE, s));
-  LTR_TRY(launch_layernorm(w.y1, 256, m->ln1g, m->ln1b, nullptr, 0, w.y1, 256, R, s));
-  float* g = w.z;  // z is dead after the V projection
-  LTR_TRY(gemm(m, m->w1, w.y1, 256, g, 1024, R, ACT_GELU, s));
-  LTR_TRY(gemm(m, m->w2, g, 1024, w.y2, 256, R, ACT_NONE, s, w.y1, 256));
+  // ---- line stage: V projection (block diagonal over heads), fc + CLS residual, LN, FFN, LN, + line pos ----
+  LTR_TRY(gemm(m->wv, w.z, 0, R, ACT_NONE, s, nullptr, 0, &w.ctx, 0));
+  LTR_TRY(gemm(m->wfc, w.ctx, 0, R, ACT_NONE, s, w.y1pre, 256));
+  LTR_TRY(launch_layernorm(w.y1pre, 256, m->ln1g, m->ln1b, nullptr, 0, w.y1, 256, w.y1i, 0, R, s));
+  LTR_TRY(gemm(m->w1, w.y1i, 0, R, ACT_GELU, s, nullptr, 0, &w.g, 0));
+  LTR_TRY(gemm(m->w2, w.g, 0, R, ACT_NONE, s, w.y2pre, 256, nullptr, 0, w.y1, 256));
   LTR_TRY(launch_small_mlp<false>(m->lpe.head, in.sublines, in.resp, in.angle, w.l128, R, in.image_width,
                                   in.image_height, s));
-  LTR_TRY(gemm(m, m->lpe.l4, w.l128, 128, w.l256, 256, R, ACT_RELU, s));
-  LTR_TRY(gemm(m, m->lpe.l5, w.l256, 256, w.lpos, 256, R, ACT_NONE, s));
-  // sentence = klines_pos + LN(ffn)  -> xm[:, :256]
-  LTR_TRY(launch_layernorm(w.y2, 256, m->ln2g, m->ln2b, w.lpos, 256, w.xm, 512, R, s));
+  LTR_TRY(gemm(m->lpe.l4, w.l128, 0, R, ACT_RELU, s, nullptr, 0, &w.l256, 0));
+  LTR_TRY(gemm(m->lpe.l5, w.l256, 0, R, ACT_NONE, s, w.lpos, 256));
+  // sentence = klines_pos + LN(ffn)  -> fp32 running descriptor xf and image xm[:, :256]
+  LTR_TRY(launch_layernorm(w.y2pre, 256, m->ln2g, m->ln2b, w.lpos, 256, w.xf, 256, w.xm, 0, R, s));
   // ---- line signature layers ----
   int max_l = in.lines_per_image;
   if (in.cu_lines_host) {
@@ -330,18 +343,18 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   }
   for (size_t li = 0; li < m->sig.size(); ++li) {
     const SigLayer& L = m->sig[li];
-    LTR_TRY(gemm(m, L.qkv, w.xm, 512, w.qkv, 768, R, ACT_NONE, s));
+    LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, w.qkv, 768));
     if (max_l > 0) {
       LaunchScope ls(KC_SIG_ATTN, s);
       dim3 grid(cdiv(max_l, SA_THREADS), 4, in.n_images);
-      sig_attention_kernel<<<grid, SA_THREADS, 0, s>>>(w.qkv, w.o, 256, cu, in.lines_per_image);
+      sig_attention_kernel<<<grid, SA_THREADS, 0, s>>>(w.qkv, w.o, cu, in.lines_per_image);
       LTR_CUDA_TRY(cudaGetLastError());
     }
-    LTR_TRY(gemm(m, L.merge, w.o, 256, w.xm + 256, 512, R, ACT_NONE, s));
-    LTR_TRY(gemm(m, L.mlp1, w.xm, 512, w.hm, 512, R, ACT_RELU, s));
-    LTR_TRY(gemm(m, L.mlp2, w.hm, 512, w.xm, 512, R, ACT_NONE, s, w.xm, 512));
+    LTR_TRY(gemm(L.merge, w.o, 0, R, ACT_NONE, s, nullptr, 0, &w.xm, 4));          // message -> xm[:, 256:]
+    LTR_TRY(gemm(L.mlp1, w.xm, 0, R, ACT_RELU, s, nullptr, 0, &w.hm, 0));
+    LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, w.xf, 256, &w.xm, 0, w.xf, 256));  // x += delta
   }
-  LTR_TRY(gemm(m, m->wf, w.xm, 512, w.yf, 256, R, ACT_NONE, s));
+  LTR_TRY(gemm(m->wf, w.xm, 0, R, ACT_NONE, s, w.yf, 256));
   if (max_l > 0) {
     LaunchScope ls(KC_FINAL_NORM, s);
     dim3 grid(cdiv(max_l, 32), in.n_images);
@@ -469,7 +482,13 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   std::vector<double> bfc_cls(D);
   for (int i = 0; i < D; ++i) bfc_cls[i] = (double)bfc[i] + cls[i];  // fc bias + CLS residual (line_attention.py:72)
   size_t oU = hp.add(U), oS = hp.add(scls), oC = hp.add(vec(cls, D));
-  LinOff oWv = hp.add_lin(vec(wv, D * D), vec(bv, D), D, D, 4);
+  // V projection of the pooled per-head inputs z = [z_0 | z_1 | z_2 | z_3] (K = 4*256) as one
+  // block-diagonal [256, 1024] matrix: output channel h*64+d only sees z_h.
+  std::vector<double> Wvbd((size_t)D * 4 * D, 0.0);
+  for (int h = 0; h < 4; ++h)
+    for (int d = 0; d < 64; ++d)
+      for (int c = 0; c < D; ++c) Wvbd[(size_t)(h * 64 + d) * (4 * D) + h * D + c] = wv[(h * 64 + d) * D + c];
+  LinOff oWv = hp.add_lin(Wvbd, vec(bv, D), D, 4 * D);
   LinOff oWfc = hp.add_lin(vec(wfc, D * D), bfc_cls, D, D);
   size_t oL1g = hp.add(vec(ln1g, D)), oL1b = hp.add(vec(ln1b, D));
   LinOff oW1 = hp.add_lin(vec(w1, (size_t)DI * D), vec(b1, DI), DI, D);
@@ -532,7 +551,7 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   bind_mlp(m->wpe, B, TB, wpe_o);
   bind_mlp(m->lpe, B, TB, lpe_o);
   m->U = B + oU; m->s_cls = B + oS; m->cls = B + oC;
-  m->wv = bind_lin(oWv, B, TB, 4);
+  m->wv = bind_lin(oWv, B, TB);
   m->wfc = bind_lin(oWfc, B, TB);
   m->ln1g = B + oL1g; m->ln1b = B + oL1b;
   m->w1 = bind_lin(oW1, B, TB);
@@ -541,7 +560,6 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   for (auto& o : so)
     m->sig.push_back({bind_lin(o.qkv, B, TB), bind_lin(o.merge, B, TB), bind_lin(o.mlp1, B, TB), bind_lin(o.mlp2, B, TB)});
   m->wf = bind_lin(oWf, B, TB);
-  if (const char* e = std::getenv("LINETR_ENGINE")) m->use_tc = std::string(e) != "f32";
   if (const char* e = std::getenv("LINETR_TOKEN_CHUNK")) {
     int v = std::atoi(e);
     if (v > 0) m->token_chunk = v;
@@ -691,6 +709,51 @@ int ltr_linear_tc(const float* x, int32_t ldx, const float* w_host, const float*
   cudaFree(d);
   if (rc != 0) return rc;
   if (ce != cudaSuccess) return set_error(LTR_E_CUDA, std::string("ltr_linear_tc: ") + cudaGetErrorString(ce));
+  return LTR_OK;
+}
+
+int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float* bias, const float* res, int32_t ldr,
+                   float* y, int32_t ldy, float* y_from_image, int32_t m, int32_t n, int32_t k, int32_t act,
+                   int32_t bn_hint, int32_t device, void* stream) {
+  if (!x || !w_host || (!y && !y_from_image)) return set_error(LTR_E_INVALID, "ltr_linear_img: null argument");
+  if (n % 128 || k % 64) return set_error(LTR_E_UNSUPPORTED, "ltr_linear_img: n %% 128 and k %% 64 required");
+  LTR_CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = as_stream(stream);
+  std::vector<double> W((size_t)n * k);
+  for (size_t i = 0; i < W.size(); ++i) W[i] = w_host[i];
+  std::vector<uint16_t> img(2 * (size_t)n * k);
+  pack_tc_weight(W.data(), n, k, img.data(), img.data() + (size_t)n * k);
+  const size_t mpad = (size_t)cdiv(m, 128) * 128;
+  uint16_t *dw = nullptr, *da = nullptr, *dout = nullptr;
+  cudaError_t ce = cudaMalloc(&dw, img.size() * 2);
+  if (ce == cudaSuccess) ce = cudaMalloc(&da, 2 * mpad * k * 2);
+  if (ce == cudaSuccess) ce = cudaMalloc(&dout, 2 * mpad * n * 2);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(dw, img.data(), img.size() * 2, cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(da, 0, 2 * mpad * k * 2, s);
+  int rc = 0;
+  if (ce == cudaSuccess) {
+    ActImg A{reinterpret_cast<__nv_bfloat16*>(da), reinterpret_cast<__nv_bfloat16*>(da + mpad * k), k / 64};
+    ActImg O{reinterpret_cast<__nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dout + mpad * n), n / 64};
+    {
+      LaunchScope ls(KC_LAYERNORM, s);
+      to_image_kernel<<<cdiv((long long)m * (k / 8), 256), 256, 0, s>>>(x, ldx, m, k, A, 0);
+    }
+    GemmImgArgs a{};
+    a.A = A; a.a_kb0 = 0; a.bias = bias; a.R = res; a.ldr = ldr; a.C = y; a.ldc = ldy; a.M = m; a.act = act;
+    a.W.hi = reinterpret_cast<const __nv_bfloat16*>(dw);
+    a.W.lo = reinterpret_cast<const __nv_bfloat16*>(dw + (size_t)n * k);
+    a.W.N = n; a.W.K = k;
+    if (y_from_image) { a.O = O; a.o_kb0 = 0; }
+    rc = launch_gemm_img(a, s, bn_hint);
+    if (rc == 0 && y_from_image) {
+      LaunchScope ls(KC_LAYERNORM, s);
+      from_image_kernel<<<cdiv((long long)m * n, 256), 256, 0, s>>>(O, 0, y_from_image, n, m, n);
+    }
+    ce = cudaStreamSynchronize(s);
+  }
+  cudaFree(dw); cudaFree(da); cudaFree(dout);
+  if (rc != 0) return rc;
+  if (ce != cudaSuccess) return set_error(LTR_E_CUDA, std::string("ltr_linear_img: ") + cudaGetErrorString(ce));
   return LTR_OK;
 }
 

@@ -211,6 +211,52 @@ class PairEngine:
                            out["dist_key"], out["stride"], d0 if keep_desc else None, d1 if keep_desc else None)
 
 
+    def match_packed(self, batch: LineBatch, n_pairs: int, nn_thresh: Optional[float] = None, mutual=True,
+                     keep_desc=False) -> PairMatches:
+        """Same as match_pairs for a batch that holds BOTH sides: images [0, P) are the side-0
+        images of the P pairs, images [P, 2P) their side-1 partners.  One `ltr_encode` over all
+        2P images (twice the rows per GEMM launch) and one `ltr_match`."""
+        P = int(n_pairs)
+        if batch.n_images != 2 * P:
+            raise ValueError("match_packed: batch must hold 2 * n_pairs images")
+        if nn_thresh is None:
+            nn_thresh = self.model.config.get("nn_threshold", 0.8)
+        rows = self.encode(batch)
+        cu = batch.cu_lines
+        R0 = int(cu[P])
+        d0, d1 = rows[:R0], rows[R0:]
+        L = batch.uniform_lines
+        if batch.sub_off is not None:
+            key = ("packed_split", str(self.device))
+            if key not in batch._dev_cache:
+                K0 = int(batch.cuk[P])
+                t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
+                batch._dev_cache[key] = dict(
+                    cu0=t(cu[:P + 1]), cu1=t(cu[P:] - cu[P]), cuk0=t(batch.cuk[:P + 1]), cuk1=t(batch.cuk[P:] - K0),
+                    sub_off0=t(batch.sub_off[:K0 + 1]), sub_off1=t(batch.sub_off[K0:] - R0),
+                    max_n0=int(np.diff(cu[:P + 1]).max(initial=0)), max_n1=int(np.diff(cu[P:]).max(initial=0)),
+                    max_k0=int(np.diff(batch.cuk[:P + 1]).max(initial=0)), max_k1=int(np.diff(batch.cuk[P:]).max(initial=0)),
+                    total_k0=K0, total_k1=int(batch.cuk[-1]) - K0)
+            kw = batch._dev_cache[key]
+            off0 = batch.cuk[:P + 1]
+        elif L is not None:
+            kw = dict(n0=L, n1=L)
+            off0 = cu[:P + 1]
+        else:
+            key = ("packed_split", str(self.device))
+            if key not in batch._dev_cache:
+                t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
+                batch._dev_cache[key] = dict(cu0=t(cu[:P + 1]), cu1=t(cu[P:] - cu[P]),
+                                             max_n0=int(np.diff(cu[:P + 1]).max(initial=0)),
+                                             max_n1=int(np.diff(cu[P:]).max(initial=0)),
+                                             total_k0=R0, total_k1=int(cu[-1]) - R0)
+            kw = batch._dev_cache[key]
+            off0 = cu[:P + 1]
+        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, **kw)
+        return PairMatches(out["matches0"], out["scores0"], out["counts"], np.asarray(off0, dtype=np.int32),
+                           out["dist_key"], out["stride"], d0 if keep_desc else None, d1 if keep_desc else None)
+
+
 # ------------------------------------------------------------------------------- multi-GPU
 def shard_range(n_items: int, rank: int, world: int):
     """Contiguous block of items owned by `rank` (sizes differ by at most one)."""

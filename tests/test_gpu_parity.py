@@ -79,6 +79,24 @@ def test_linear_tensor_core_engine_vs_fp64(M, N_, K, act):
     assert err < 1e-4, err
 
 
+@pytest.mark.parametrize("M,N_,K,act,bn", [(1, 128, 64, 0, 0), (128, 128, 64, 0, 128), (127, 256, 128, 1, 256),
+                                           (300, 768, 256, 0, 256), (513, 1024, 256, 2, 0), (64, 256, 1024, 0, 128),
+                                           (40000, 256, 256, 0, 256), (20000, 512, 512, 1, 0), (1000, 256, 512, 0, 128)])
+def test_persistent_image_gemm_vs_fp64(M, N_, K, act, bn):
+    """gemm_img engine: TMA-fed split-bf16 tile images in, fp32 rows + split-bf16 image out,
+    persistent CTAs with double-buffered TMEM accumulators (more tiles than SMs at M=40000)."""
+    g = torch.Generator().manual_seed(M * 7 + K + N_)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N_, K, generator=g) / K ** 0.5
+    b = torch.randn(N_, generator=g)
+    r = torch.randn(M, N_, generator=g)
+    want = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    want = [want, torch.relu(want), torch.nn.functional.gelu(want)][act] + r.double()
+    y, y_img = _ops.linear_img(x.to(DEV), w, b.to(DEV), r.to(DEV), act, bn)
+    assert (y.cpu().double() - want).abs().max().item() < 1e-4
+    assert (y_img.cpu().double() - want).abs().max().item() < 2e-4     # + split-bf16 re-quantisation of the output
+
+
 # ------------------------------------------------------------------ encoder
 @pytest.mark.parametrize("name", H.ENC_CASES)
 def test_forward_vs_reference_golden_and_oracle(name):
@@ -267,6 +285,24 @@ def test_pair_batch_with_keyline_merging_vs_oracle():
         K0, K1 = dk.shape[1:]
         got = res.dist[p * res.stride:p * res.stride + K0 * K1].view(K0, K1).cpu().numpy()
         assert np.abs(got - dk[0]).max() < 1e-3
+
+
+def test_match_packed_equals_match_pairs():
+    model, sd = model_for("synthetic:0:1")
+    eng = engine.PairEngine(model, DEV)
+    for uniform in (True, False):
+        pairs = []
+        for p in range(3):
+            L = 40 if uniform else 20 + 7 * p
+            a, b, _ = syn.make_pair_inputs(400 + p, L, 21, n_lines1=L if uniform else L - p)
+            pairs.append((a, b))
+        r1 = eng.match_pairs(engine.LineBatch.from_images([a for a, _ in pairs]).to(DEV),
+                             engine.LineBatch.from_images([b for _, b in pairs]).to(DEV), 0.8)
+        r2 = eng.match_packed(engine.LineBatch.from_images([a for a, _ in pairs] + [b for _, b in pairs]).to(DEV), 3, 0.8)
+        assert torch.equal(r1.matches0, r2.matches0) and torch.equal(r1.counts, r2.counts)
+        for p, (a, b) in enumerate(pairs):
+            mat, _, _, _ = orc.match_pair(sd, a, b, 0.8)
+            assert np.array_equal(r2.pair(p).cpu().numpy(), orc.match_indices(mat))
 
 
 def test_shipped_checkpoint_cfg1_pair():
