@@ -305,6 +305,19 @@ def test_match_packed_equals_match_pairs():
             assert np.array_equal(r2.pair(p).cpu().numpy(), orc.match_indices(mat))
 
 
+def test_host_pipelined_entry_equals_resident():
+    model, sd = model_for("synthetic:0:1")
+    eng = engine.PairEngine(model, DEV)
+    pairs = [syn.make_pair_inputs(500 + p, 16 + 5 * p, 21, n_lines1=16 + 4 * p)[:2] for p in range(5)]
+    host = engine.LineBatch.from_images([a for a, _ in pairs] + [b for _, b in pairs]).pin()
+    want = eng.match_packed(host.to(DEV), 5, 0.8)
+    for chunks in (1, 2, 5):
+        m0, cnt, off = eng.match_packed_host(host, 5, 0.8, n_chunks=chunks)
+        torch.cuda.synchronize()
+        assert torch.equal(m0, want.matches0) and torch.equal(cnt, want.counts)
+        assert np.array_equal(off, want.offsets0)
+
+
 def test_shipped_checkpoint_cfg1_pair():
     npz, meta = H.golden()
     model, sd = model_for("shipped")
