@@ -12,6 +12,7 @@
 #include "linear_f32.cuh"
 #include "linear_tc.cuh"
 #include "gemm_img.cuh"
+#include "token_fused.cuh"
 #include "match_kernels.cuh"
 
 namespace ltr {
@@ -54,7 +55,7 @@ struct Lin {
 
 struct MlpTail {  // positional encoder: narrow head + the two wide layers (128->256 relu, 256->256)
   SmallMlpWeights head;
-  Lin l4, l5;
+  Lin l3, l4, l5;
 };
 
 struct SigLayer {
@@ -156,7 +157,7 @@ static bool fold_layer(const TensorMap& tm, const std::string& conv, const std::
   return true;
 }
 
-struct MlpOffsets { size_t w[3], b[3]; LinOff l4, l5; };
+struct MlpOffsets { size_t w[3], b[3]; LinOff l3, l4, l5; };
 
 static bool pack_pos_encoder(const TensorMap& tm, const std::string& prefix, int in, HostPack& hp, MlpOffsets& off,
                              std::string& err) {
@@ -169,6 +170,7 @@ static bool pack_pos_encoder(const TensorMap& tm, const std::string& prefix, int
     if (l < 3) {
       off.w[l] = hp.add(W);
       off.b[l] = hp.add(b);
+      if (l == 2) off.l3 = hp.add_lin(W, b, ch[l + 1], ch[l]);  // 64 -> 128 also as a tensor-core image
     } else if (l == 3) {
       off.l4 = hp.add_lin(W, b, ch[l + 1], ch[l]);
     } else {
@@ -182,6 +184,7 @@ static void bind_mlp(MlpTail& m, float* base, uint16_t* tbase, const MlpOffsets&
   m.head.w1 = base + o.w[0]; m.head.b1 = base + o.b[0];
   m.head.w2 = base + o.w[1]; m.head.b2 = base + o.b[1];
   m.head.w3 = base + o.w[2]; m.head.b3 = base + o.b[2];
+  m.l3 = bind_lin(o.l3, base, tbase);
   m.l4 = bind_lin(o.l4, base, tbase);
   m.l5 = bind_lin(o.l5, base, tbase);
 }
@@ -190,9 +193,6 @@ static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 // ------------------------------------------------------------------ workspace
 struct EncodeWs {
-  // token stage, one chunk of lines (kept L2 resident)
-  ActImg h128, h256;   // images [chunk tokens, 128 / 256]
-  float* x;            // fp32 [chunk tokens, 256] = desc + word positional encoding
   // line stage
   ActImg z, ctx, y1i, g, l128, l256;  // images [R, 1024 / 256 / 256 / 1024 / 128 / 256]
   float *y1pre, *y1, *y2pre, *lpos;   // fp32 [R, 256]
@@ -220,14 +220,9 @@ static EncodeWs carve(const LtrModel* m, int n_lines, int T, char* base) {
     a.kblocks = K / 64;
     return a;
   };
-  int cl = m->token_chunk / T;
-  if (cl < 1) cl = 1;
-  if (cl > n_lines) cl = n_lines > 0 ? n_lines : 1;
-  w.chunk_lines = cl;
-  const int64_t ct = (int64_t)cl * T, R = n_lines;
-  w.h128 = takei(ct, 128);
-  w.h256 = takei(ct, 256);
-  w.x = takef(ct * 256);
+  (void)m; (void)T;
+  w.chunk_lines = 0;
+  const int64_t R = n_lines;
   w.z = takei(R, 1024);
   w.ctx = takei(R, 256);
   w.y1i = takei(R, 256);
@@ -307,21 +302,18 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
                        cudaStream_t s) {
   const int R = in.n_lines, T = in.n_tokens;
   const int* cu = in.cu_lines_dev;
-  // ---- token stage, chunked over lines so that the intermediates stay L2 resident ----
-  for (int l0 = 0; l0 < R; l0 += w.chunk_lines) {
-    const int nl = std::min(w.chunk_lines, R - l0);
-    const int rows = nl * T;
-    const int64_t t0 = (int64_t)l0 * T;
-    LTR_TRY(launch_small_mlp<true>(m->wpe.head, in.pnt + t0 * 2, in.score + t0, nullptr, w.h128, rows, in.image_width,
-                                   in.image_height, s));
-    LTR_TRY(gemm(m->wpe.l4, w.h128, 0, rows, ACT_RELU, s, nullptr, 0, &w.h256, 0));
-    // x = desc + word_position_enc  (line_transformer.py:117)
-    LTR_TRY(gemm(m->wpe.l5, w.h256, 0, rows, ACT_NONE, s, w.x, 256, nullptr, 0, in.desc + t0 * 256, 256));
-    {
-      LaunchScope ls(KC_CLS_POOL, s);
-      cls_pool_kernel<<<nl, CP_THREADS, 0, s>>>(w.x, m->U, m->s_cls, m->cls, w.z, l0, T);
-      LTR_CUDA_TRY(cudaGetLastError());
-    }
+  // ---- token stage: one fused persistent kernel (narrow MLP, 3 tensor-core layers, + desc, CLS pooling) ----
+  {
+    TokenFusedArgs a{};
+    a.pnt = in.pnt; a.score = in.score; a.desc = in.desc;
+    a.w1 = m->wpe.head.w1; a.b1 = m->wpe.head.b1; a.w2 = m->wpe.head.w2; a.b2 = m->wpe.head.b2;
+    a.W3 = m->wpe.l3.tw; a.W4 = m->wpe.l4.tw; a.W5 = m->wpe.l5.tw;
+    a.b3 = m->wpe.l3.b; a.b4 = m->wpe.l4.b; a.b5 = m->wpe.l5.b;
+    a.U = m->U; a.s_cls = m->s_cls; a.cls = m->cls;
+    a.z = w.z; a.R = R; a.T = T;
+    a.cx = in.image_width / 2.f; a.cy = in.image_height / 2.f;
+    a.scale = fmaxf(in.image_width, in.image_height) * 0.7f;
+    LTR_TRY(launch_token_fused(a, s));
   }
   // ---- line stage: V projection (block diagonal over heads), fc + CLS residual, LN, FFN, LN, + line pos ----
   LTR_TRY(gemm(m->wv, w.z, 0, R, ACT_NONE, s, nullptr, 0, &w.ctx, 0));

@@ -1,0 +1,380 @@
+// Fused token stage of the line-descriptor forward (sm_100a, tcgen05 + TMA).
+//
+// One persistent CTA per SM walks tiles of LPT = floor(128 / T) whole lines (LPT*T <= 128 token
+// rows).  Per tile, entirely on chip:
+//   P0  narrow positional MLP 3 -> 32 -> 64 (+ReLU) on CUDA cores            -> h64  (smem, split-bf16)
+//   L3  64 -> 128 (+ReLU)   tcgen05, accumulator in TMEM, epilogue -> smem   -> h128
+//   L4  128 -> 256 (+ReLU)  tcgen05                                          -> h256
+//   L5  256 -> 256          tcgen05, epilogue adds the sampled descriptors   -> x = desc + wpe (fp32, smem)
+//   CLS pooling: folded CLS-query scores x.u_h, softmax over the T tokens + CLS per head,
+//       z_h = sum_n p_h[n] x[n]                                               -> z image (global)
+// Replaces WordPositionalEncoder (models/line_transformer.py:61-73), `desc + pos` and the CLS
+// concat (:117-121) and the attention part of MultiHeadAttention restricted to the CLS query row
+// (models/line_attention.py:13-21,55-63), i.e. what small_mlp_kernel<true> + 2 GEMM launches +
+// cls_pool_kernel did through global memory.  Only `desc` (the mandatory HBM read), the
+// weights (L2 resident, streamed by TMA through a 2-slot ring) and the pooled z leave/enter the SM.
+//
+// Warp roles: warp 0 = TMA weight producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-9 =
+// 256 worker threads (thread pair per token row: lane = row within the warp's TMEM lane
+// quarter, `half` = which half of the output columns).
+#pragma once
+#include "act_img.cuh"
+#include "common.cuh"
+#include "linear_tc.cuh"
+#include "ptx_sm100.cuh"
+
+namespace ltr {
+
+struct TokenFusedArgs {
+  const float* pnt;    // [R*T, 2]
+  const float* score;  // [R*T]
+  const float* desc;   // [R*T, 256]
+  // narrow layers (fp32, BN folded): w1 [32,3], w2 [64,32]
+  const float *w1, *b1, *w2, *b2;
+  TcWeight W3, W4, W5;  // [128,64], [256,128], [256,256] packed split-bf16
+  const float *b3, *b4, *b5;
+  const float* U;      // [4,256] folded CLS query (see cls_pool_kernel)
+  const float* s_cls;  // [4]
+  const float* cls;    // [256]
+  ActImg z;            // out: image of [R, 1024]
+  int R, T, lpt, n_tiles;
+  float cx, cy, scale;
+};
+
+struct TokenFusedSmem {
+  static constexpr int ACT = 128 * 1024;   // activation region: h64/h128/h256 images, then x fp32
+  static constexpr int SLOT = 32 * 1024;   // one W tile [128 n x 64 k] hi + lo
+  static constexpr int NSLOT = 2;
+  static constexpr int OFF_RING = ACT;
+  static constexpr int OFF_W1 = OFF_RING + NSLOT * SLOT;   // 96 floats
+  static constexpr int OFF_B1 = OFF_W1 + 96 * 4;           // 32
+  static constexpr int OFF_W2 = OFF_B1 + 32 * 4;           // 64*32
+  static constexpr int OFF_B2 = OFF_W2 + 2048 * 4;         // 64
+  static constexpr int OFF_B3 = OFF_B2 + 64 * 4;           // 128
+  static constexpr int OFF_B4 = OFF_B3 + 128 * 4;          // 256
+  static constexpr int OFF_B5 = OFF_B4 + 256 * 4;          // 256
+  static constexpr int OFF_U = OFF_B5 + 256 * 4;           // 1024
+  static constexpr int OFF_CLS = OFF_U + 1024 * 4;         // 256
+  static constexpr int OFF_SC = OFF_CLS + 256 * 4;         // partial scores [2][128][4]
+  static constexpr int OFF_P = OFF_SC + 2 * 128 * 4 * 4;   // probabilities [128][4] + cls [lpt <= 128][4]
+  static constexpr int OFF_BAR = OFF_P + (128 + 128) * 4 * 4;
+  static constexpr int TOTAL = OFF_BAR + 128 + 1024;       // + alignment slack
+};
+
+// x tile in the activation region: fp32 [128 rows][256], 16-byte chunks XOR-swizzled by row & 7
+__device__ __forceinline__ int xs_index(int row, int col) {
+  return row * 256 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
+}
+
+__global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
+  using S = TokenFusedSmem;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* act = smem;
+  float* sW1 = reinterpret_cast<float*>(smem + S::OFF_W1);
+  float* sB1 = reinterpret_cast<float*>(smem + S::OFF_B1);
+  float* sW2 = reinterpret_cast<float*>(smem + S::OFF_W2);
+  float* sB2 = reinterpret_cast<float*>(smem + S::OFF_B2);
+  float* sB3 = reinterpret_cast<float*>(smem + S::OFF_B3);
+  float* sB4 = reinterpret_cast<float*>(smem + S::OFF_B4);
+  float* sB5 = reinterpret_cast<float*>(smem + S::OFF_B5);
+  float* sU = reinterpret_cast<float*>(smem + S::OFF_U);
+  float* sCls = reinterpret_cast<float*>(smem + S::OFF_CLS);
+  float* sSc = reinterpret_cast<float*>(smem + S::OFF_SC);
+  float* sP = reinterpret_cast<float*>(smem + S::OFF_P);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* full = bars;            // [2] W slot filled (TMA tx)
+  uint64_t* empty = bars + 2;       // [2] W slot consumed (tcgen05.commit)
+  uint64_t* a_ready = bars + 4;     // workers -> MMA: A operand image complete (256 arrivals)
+  uint64_t* acc_ready = bars + 5;   // MMA -> workers: accumulator complete (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < 96; i += blockDim.x) sW1[i] = p.w1[i];
+  for (int i = tid; i < 32; i += blockDim.x) sB1[i] = p.b1[i];
+  for (int i = tid; i < 2048; i += blockDim.x) sW2[i] = p.w2[i];
+  for (int i = tid; i < 64; i += blockDim.x) sB2[i] = p.b2[i];
+  for (int i = tid; i < 128; i += blockDim.x) sB3[i] = p.b3[i];
+  for (int i = tid; i < 256; i += blockDim.x) { sB4[i] = p.b4[i]; sB5[i] = p.b5[i]; sCls[i] = p.cls[i]; }
+  for (int i = tid; i < 1024; i += blockDim.x) sU[i] = p.U[i];
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(a_ready, 256);
+    ptx::mbar_init(acc_ready, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- W producer: 13 slots per tile
+    if (lane == 0) {
+      uint32_t it = 0;
+      auto push = [&](const TcWeight& W, int nb, int kb) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* dst = smem + S::OFF_RING + s * S::SLOT;
+        const size_t off = ((size_t)kb * (W.N / 8) + (size_t)nb * 16) * 1024;
+        ptx::mbar_arrive_expect_tx(&full[s], S::SLOT);
+        ptx::bulk_g2s(dst, reinterpret_cast<const uint8_t*>(W.hi) + off, 16384, &full[s]);
+        ptx::bulk_g2s(dst + 16384, reinterpret_cast<const uint8_t*>(W.lo) + off, 16384, &full[s]);
+        ++it;
+      };
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        push(p.W3, 0, 0);
+        for (int nb = 0; nb < 2; ++nb)
+          for (int kb = 0; kb < 2; ++kb) push(p.W4, nb, kb);
+        for (int nb = 0; nb < 2; ++nb)
+          for (int kb = 0; kb < 4; ++kb) push(p.W5, nb, kb);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 128);
+      const uint32_t act_u = ptx::smem_u32(act);
+      uint32_t it = 0, na = 0;
+      // one [128 x 128 x 64] block: A k-block kb of an activation with nkb k-blocks, W from the ring
+      auto block = [&](int nkb, int kb, int nb, bool first) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t a_hi = act_u + kb * 16384, a_lo = act_u + (nkb + kb) * 16384;
+        const uint32_t w_hi = ptx::smem_u32(smem + S::OFF_RING + s * S::SLOT), w_lo = w_hi + 16384;
+        const uint32_t d = tmem_base + nb * 128;
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+          const uint32_t ko = k16 * 32;
+          const uint64_t dah = ptx::make_sw128_kmajor_desc(a_hi + ko, 1024);
+          const uint64_t dal = ptx::make_sw128_kmajor_desc(a_lo + ko, 1024);
+          const uint64_t dwh = ptx::make_sw128_kmajor_desc(w_hi + ko, 1024);
+          const uint64_t dwl = ptx::make_sw128_kmajor_desc(w_lo + ko, 1024);
+          ptx::umma_bf16(d, dal, dwh, idesc, !(first && k16 == 0));
+          ptx::umma_bf16(d, dah, dwl, idesc, 1);
+          ptx::umma_bf16(d, dah, dwh, idesc, 1);
+        }
+        ptx::umma_commit(&empty[s]);
+        ++it;
+      };
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(a_ready, na++ & 1);   // h64
+        ptx::tc_fence_after();
+        block(1, 0, 0, true);
+        ptx::umma_commit(acc_ready);
+        ptx::mbar_wait(a_ready, na++ & 1);   // h128
+        ptx::tc_fence_after();
+        for (int nb = 0; nb < 2; ++nb)
+          for (int kb = 0; kb < 2; ++kb) block(2, kb, nb, kb == 0);
+        ptx::umma_commit(acc_ready);
+        ptx::mbar_wait(a_ready, na++ & 1);   // h256
+        ptx::tc_fence_after();
+        for (int nb = 0; nb < 2; ++nb)
+          for (int kb = 0; kb < 4; ++kb) block(4, kb, nb, kb == 0);
+        ptx::umma_commit(acc_ready);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- workers (256 threads)
+    const int q = warp & 3;            // TMEM lane quarter
+    const int half = (warp - 2) >> 2;  // column half
+    const int r_in = q * 32 + lane;    // token row inside the tile
+    const int wt = tid - 64;           // 0..255
+    const int rows_used = p.lpt * p.T;
+    uint32_t nacc = 0;
+    auto worker_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // split-bf16 store of 8 consecutive columns into an activation image with nkb k-blocks
+    auto act_store8 = [&](int nkb, int col, const float (&v)[8]) {
+      __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ptx::split_bf16(v[e], h[e], l[e]);
+      const uint32_t off = (col >> 6) * 16384 + ptx::sw128_offset(r_in, col & 63);
+      *reinterpret_cast<uint4*>(act + off) =
+          make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
+      *reinterpret_cast<uint4*>(act + nkb * 16384 + off) =
+          make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+    };
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int line0 = tile * p.lpt;
+      const long long tok0 = (long long)line0 * p.T;
+      const long long n_tok_total = (long long)p.R * p.T;
+      const bool row_live = r_in < rows_used && tok0 + r_in < n_tok_total;
+      // ---- P0: 3 -> 32 -> 64 for this row, this thread produces outputs [32*half, 32*half+32)
+      {
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        if (row_live) {
+          const long long t = tok0 + r_in;
+          x0 = (p.pnt[2 * t] - p.cx) / p.scale;
+          x1 = (p.pnt[2 * t + 1] - p.cy) / p.scale;
+          x2 = p.score[t];
+        }
+        float h1[32];
+#pragma unroll
+        for (int n = 0; n < 32; ++n)
+          h1[n] = fmaxf(fmaf(sW1[n * 3 + 2], x2, fmaf(sW1[n * 3 + 1], x1, fmaf(sW1[n * 3], x0, sB1[n]))), 0.f);
+#pragma unroll 1
+        for (int n0 = 0; n0 < 32; n0 += 8) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = half * 32 + n0 + j;
+            float a = sB2[n];
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(&sW2[n * 32 + k]);
+              a = fmaf(w.x, h1[k], a); a = fmaf(w.y, h1[k + 1], a);
+              a = fmaf(w.z, h1[k + 2], a); a = fmaf(w.w, h1[k + 3], a);
+            }
+            o[j] = fmaxf(a, 0.f);
+          }
+          act_store8(1, half * 32 + n0, o);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(a_ready);
+      // ---- epilogue L3: 128 columns (64 per half) -> h128
+      ptx::mbar_wait(acc_ready, nacc++ & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+        float acc[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = fmaxf(acc[j + e] + sB3[c0 + j + e], 0.f);
+          act_store8(2, c0 + j, o);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(a_ready);
+      // ---- epilogue L4: 256 columns (128 per half) -> h256
+      ptx::mbar_wait(acc_ready, nacc++ & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        float acc[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = fmaxf(acc[j + e] + sB4[c0 + j + e], 0.f);
+          act_store8(4, c0 + j, o);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(a_ready);
+      // ---- epilogue L5: x = acc + b5 + desc -> fp32 tile in the (now dead) activation region,
+      //      partial CLS scores over this thread's 128 columns
+      ptx::mbar_wait(acc_ready, nacc++ & 1);
+      ptx::tc_fence_after();
+      float* xs = reinterpret_cast<float*>(act);
+      float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
+      const float* drow = p.desc + (tok0 + r_in) * 256;
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        float acc[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = c0 + j;
+          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_live) d = __ldg(reinterpret_cast<const float4*>(drow + n));
+          float4 x;
+          x.x = acc[j] + sB5[n] + d.x;
+          x.y = acc[j + 1] + sB5[n + 1] + d.y;
+          x.z = acc[j + 2] + sB5[n + 2] + d.z;
+          x.w = acc[j + 3] + sB5[n + 3] + d.w;
+          *reinterpret_cast<float4*>(&xs[xs_index(r_in, n)]) = x;
+          const float4 u0 = *reinterpret_cast<const float4*>(&sU[n]);
+          const float4 u1 = *reinterpret_cast<const float4*>(&sU[256 + n]);
+          const float4 u2 = *reinterpret_cast<const float4*>(&sU[512 + n]);
+          const float4 u3 = *reinterpret_cast<const float4*>(&sU[768 + n]);
+          sc0 = fmaf(x.x, u0.x, fmaf(x.y, u0.y, fmaf(x.z, u0.z, fmaf(x.w, u0.w, sc0))));
+          sc1 = fmaf(x.x, u1.x, fmaf(x.y, u1.y, fmaf(x.z, u1.z, fmaf(x.w, u1.w, sc1))));
+          sc2 = fmaf(x.x, u2.x, fmaf(x.y, u2.y, fmaf(x.z, u2.z, fmaf(x.w, u2.w, sc2))));
+          sc3 = fmaf(x.x, u3.x, fmaf(x.y, u3.y, fmaf(x.z, u3.z, fmaf(x.w, u3.w, sc3))));
+        }
+      }
+      ptx::tc_fence_before();
+      *reinterpret_cast<float4*>(&sSc[(half * 128 + r_in) * 4]) = make_float4(sc0, sc1, sc2, sc3);
+      worker_sync();
+      // ---- softmax over the T tokens + CLS of every (line, head): threads 0 .. 4*lpt-1
+      for (int pi = wt; pi < 4 * p.lpt; pi += 256) {
+        const int ln = pi >> 2, h = pi & 3;
+        const int rb = ln * p.T;
+        float m = p.s_cls[h];
+        for (int n = 0; n < p.T; ++n) m = fmaxf(m, sSc[(rb + n) * 4 + h] + sSc[(128 + rb + n) * 4 + h]);
+        float e0 = expf(p.s_cls[h] - m), sum = e0;
+        for (int n = 0; n < p.T; ++n) {
+          const float e = expf(sSc[(rb + n) * 4 + h] + sSc[(128 + rb + n) * 4 + h] - m);
+          sP[(rb + n) * 4 + h] = e;
+          sum += e;
+        }
+        const float inv = 1.f / sum;
+        for (int n = 0; n < p.T; ++n) sP[(rb + n) * 4 + h] *= inv;
+        sP[(128 + ln) * 4 + h] = e0 * inv;
+      }
+      worker_sync();
+      // ---- pooling: thread = channel; z_h[c] = p_cls * cls[c] + sum_n p[n] x[n][c]
+      {
+        const int c = wt;
+        const float cv = sCls[c];
+        for (int ln = 0; ln < p.lpt; ++ln) {
+          const int gl = line0 + ln;
+          if (gl >= p.R) break;
+          const float4 pc = *reinterpret_cast<const float4*>(&sP[(128 + ln) * 4]);
+          float z0 = pc.x * cv, z1 = pc.y * cv, z2 = pc.z * cv, z3 = pc.w * cv;
+          const int rb = ln * p.T;
+          for (int n = 0; n < p.T; ++n) {
+            const float xv = xs[xs_index(rb + n, c)];
+            const float4 pr = *reinterpret_cast<const float4*>(&sP[(rb + n) * 4]);
+            z0 = fmaf(pr.x, xv, z0); z1 = fmaf(pr.y, xv, z1);
+            z2 = fmaf(pr.z, xv, z2); z3 = fmaf(pr.w, xv, z3);
+          }
+          img_store1(p.z, gl, c, z0);
+          img_store1(p.z, gl, 256 + c, z1);
+          img_store1(p.z, gl, 512 + c, z2);
+          img_store1(p.z, gl, 768 + c, z3);
+        }
+      }
+      worker_sync();   // x tile and probabilities are dead: the next tile may overwrite them
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+inline int launch_token_fused(TokenFusedArgs a, cudaStream_t s) {
+  if (a.R <= 0) return 0;
+  if (a.T < 1 || a.T > 128) return set_error(-1, "token_fused: T must be in 1..128");
+  static bool attr_set = false;
+  if (!attr_set) {
+    LTR_CUDA_TRY(cudaFuncSetAttribute(token_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TokenFusedSmem::TOTAL));
+    attr_set = true;
+  }
+  a.lpt = 128 / a.T;
+  a.n_tiles = cdiv(a.R, a.lpt);
+  const int sms = 148;
+  const int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  LaunchScope ls(KC_TOKEN_FUSED, s);
+  token_fused_kernel<<<grid, 320, TokenFusedSmem::TOTAL, s>>>(a);
+  LTR_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ltr
