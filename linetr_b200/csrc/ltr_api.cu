@@ -13,6 +13,7 @@
 #include "linear_tc.cuh"
 #include "gemm_img.cuh"
 #include "token_fused.cuh"
+#include "sig_attention_tc.cuh"
 #include "match_kernels.cuh"
 
 namespace ltr {
@@ -336,12 +337,7 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   for (size_t li = 0; li < m->sig.size(); ++li) {
     const SigLayer& L = m->sig[li];
     LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, w.qkv, 768));
-    if (max_l > 0) {
-      LaunchScope ls(KC_SIG_ATTN, s);
-      dim3 grid(cdiv(max_l, SA_THREADS), 4, in.n_images);
-      sig_attention_kernel<<<grid, SA_THREADS, 0, s>>>(w.qkv, w.o, cu, in.lines_per_image);
-      LTR_CUDA_TRY(cudaGetLastError());
-    }
+    LTR_TRY(launch_sig_attention_tc(w.qkv, w.o, cu, in.lines_per_image, max_l, in.n_images, s));
     LTR_TRY(gemm(L.merge, w.o, 0, R, ACT_NONE, s, nullptr, 0, &w.xm, 4));          // message -> xm[:, 256:]
     LTR_TRY(gemm(L.mlp1, w.xm, 0, R, ACT_RELU, s, nullptr, 0, &w.hm, 0));
     LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, w.xf, 256, &w.xm, 0, w.xf, 256));  // x += delta
