@@ -192,6 +192,16 @@ int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float
                    int32_t m, int32_t n, int32_t k, int32_t act, int32_t bn_hint, int32_t device,
                    void* stream);
 
+/* Micro-benchmark of the image-operand GEMM engine (zero-filled operands, timing only):
+ * average device milliseconds per launch.  out_mode: 0 fp32 rows, 1 image, 2 both. */
+float ltr_gemm_bench(int32_t m, int32_t n, int32_t k, int32_t bn_hint, int32_t out_mode, int32_t iters,
+                     int32_t device);
+
+/* clock64 stamps of CTA 0 recorded by the last ltr_gemm_bench call (64 slots, 16 per tile:
+ * 0 MMA acc_empty ok, 1 first operands landed, 2 MMAs issued, 3 epilogue acc_full ok, 4 first
+ * TMEM chunk read, 5 epilogue done, 6 producer slot free).  Debug aid. */
+const unsigned long long* ltr_gemm_trace(void);
+
 /* Instrumentation.  Kernel launches issued by this library since the last reset. */
 int64_t ltr_launch_count(void);
 void ltr_reset_launch_count(void);

@@ -33,7 +33,10 @@ struct GemmImgArgs {
   ActImg O; int o_kb0;       // image output (O.hi == nullptr: none); column n -> k-block o_kb0 + n/64
   int M, act;
   int m_tiles, n_blks;
+  unsigned long long* trace;   // debug: clock64 stamps of CTA 0 (nullptr = off)
 };
+
+#define LTR_STAMP(slot) do { if (p.trace && blockIdx.x == 0) p.trace[slot] = clock64(); } while (0)
 
 template <int BN>
 struct GemmImgCfg {
@@ -41,7 +44,10 @@ struct GemmImgCfg {
   static constexpr int W_TILE = BN * 128;         // one plane of a BN x 64 bf16 tile
   static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
   static constexpr int STAGES = BN >= 256 ? 2 : 3;
-  static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
+  static constexpr int STG_WARP = 4096;           // per epilogue warp: 32 rows x 32 fp32 (or 2 x [32 x 64 B] bf16)
+  static constexpr int OFF_STG = STAGES * STAGE;
+  static constexpr int OFF_BAR = OFF_STG + 8 * STG_WARP;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;        // two accumulators
   static constexpr int THREADS = 320;             // TMA warp, MMA warp, 8 epilogue warps
 };
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* acc_full = bars + 2 * Cfg::STAGES;
@@ -95,6 +101,7 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
           const int s = it % Cfg::STAGES;
           const uint32_t ph = (it / Cfg::STAGES) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1);
+          if (it < 4) LTR_STAMP(it * 16 + 6);
           uint8_t* st = smem + s * Cfg::STAGE;
           const size_t aoff = ((size_t)mt * p.A.kblocks + p.a_kb0 + kb) * IMG_TILE_ELEMS;
           const size_t woff = ((size_t)kb * (p.W.N / 8) + (size_t)nb * (BN / 8)) * 1024;
@@ -115,12 +122,14 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
         const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
         ptx::mbar_wait(&acc_empty[buf], aph ^ 1);
         ptx::tc_fence_after();
+        if (tl < 4) LTR_STAMP(tl * 16 + 0);
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
           const uint32_t ph = (it / Cfg::STAGES) & 1;
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
+          if (tl < 4 && kb == 0) LTR_STAMP(tl * 16 + 1);
           const uint32_t a_hi = ptx::smem_u32(smem + s * Cfg::STAGE);
           const uint32_t a_lo = a_hi + Cfg::A_TILE;
           const uint32_t w_hi = a_hi + 2 * Cfg::A_TILE;
@@ -139,62 +148,134 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
           ptx::umma_commit(&empty[s]);
         }
         ptx::umma_commit(&acc_full[buf]);
+        if (tl < 4) LTR_STAMP(tl * 16 + 2);
       }
     }
   } else {
     // ---------------------------------------------------------------- epilogue (8 warps)
-    const int q = warp & 3;           // TMEM lane quarter this warp may read
+    // A thread owns one accumulator row (TMEM lane).  Global traffic goes through a per-warp
+    // 4 KB staging tile so that every global load/store instruction of a warp touches whole
+    // 32-byte sectors of a few rows instead of 16 bytes of 32 different rows.
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;  // which half of the BN columns
+    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (warp - 2) * Cfg::STG_WARP);
+    uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
       const int mt = tile / p.n_blks, nb = tile - mt * p.n_blks;
       const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
       ptx::mbar_wait(&acc_full[buf], aph);
       ptx::tc_fence_after();
-      const int r_in = q * 32 + lane;
-      const int row = mt * 128 + r_in;
-      const bool live = row < p.M;
+      if (tl < 4 && warp == 2 && lane == 0) LTR_STAMP(tl * 16 + 3);
+      const int row0 = mt * 128 + q * 32;   // first row of this warp
+#ifdef LTR_EPI_LD64_EXPERIMENT
+      if (!p.C && !p.O.hi) {   // timing experiment: drain the accumulator with 64-column loads only
+        float sink = 0.f;
+        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 64) {
+          float a64[64];
+          ptx::tmem_ld64(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c0, a64);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) sink += a64[j];
+        }
+        if (sink == 123.456f && p.trace) p.trace[63] = 1;
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (tl < 4 && warp == 2 && lane == 0) LTR_STAMP(tl * 16 + 5);
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
+#endif
 #pragma unroll 1
       for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         float acc[32];
         ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c0, acc);
-        if (live) {
-          const int nbase = nb * BN + c0;
+        if (tl < 4 && warp == 2 && lane == 0 && c0 == 0) LTR_STAMP(tl * 16 + 4);
+        const int nbase = nb * BN + c0;
+        if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const int n = nbase + j;
-            const float4 b = p.bias ? *reinterpret_cast<const float4*>(p.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[j] = apply_act(acc[j] + b.x, p.act);
-            acc[j + 1] = apply_act(acc[j + 1] + b.y, p.act);
-            acc[j + 2] = apply_act(acc[j + 2] + b.z, p.act);
-            acc[j + 3] = apply_act(acc[j + 3] + b.w, p.act);
-            if (p.R) {
-              const float4 rr = *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + n);
-              acc[j] += rr.x; acc[j + 1] += rr.y; acc[j + 2] += rr.z; acc[j + 3] += rr.w;
-            }
-            if (p.C) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + n) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + nbase + j);
+            acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
           }
-          if (p.O.hi) {
-            const int kb_out = p.o_kb0 + (nbase >> 6);
-            const size_t toff = ((size_t)mt * p.O.kblocks + kb_out) * IMG_TILE_ELEMS;
-            uint8_t* ohi = reinterpret_cast<uint8_t*>(p.O.hi + toff);
-            uint8_t* olo = reinterpret_cast<uint8_t*>(p.O.lo + toff);
+        }
+        // the activation is uniform per launch: branch ONCE per chunk (an if-converted erff per
+        // element costs ~40 instructions even when ReLU/identity is selected)
+        if (p.act == ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __nv_bfloat16 h[8], l[8];
+          for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        } else if (p.act == ACT_GELU) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) ptx::split_bf16(acc[j + e], h[e], l[e]);
-              const uint32_t off = ptx::sw128_offset(r_in, (nbase & 63) + j);
-              *reinterpret_cast<uint4*>(ohi + off) =
-                  make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
-              *reinterpret_cast<uint4*>(olo + off) =
-                  make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+          for (int j = 0; j < 32; ++j) acc[j] = 0.5f * acc[j] * (1.f + erff(acc[j] * 0.70710678118654752440f));
+        }
+        if (p.R) {
+          // coalesced read of the 32 x 32 residual tile: lane -> (row i*4 + lane/8, float4 lane%8)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + (lane >> 3), c4 = lane & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + rl < p.M) v = *reinterpret_cast<const float4*>(p.R + (long long)(row0 + rl) * p.ldr + nbase + c4 * 4);
+            *reinterpret_cast<float4*>(&stg[rl * 32 + ((c4 ^ (rl & 7)) << 2)]) = v;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 v = *reinterpret_cast<const float4*>(&stg[lane * 32 + ((c4 ^ (lane & 7)) << 2)]);
+            acc[c4 * 4] += v.x; acc[c4 * 4 + 1] += v.y; acc[c4 * 4 + 2] += v.z; acc[c4 * 4 + 3] += v.w;
+          }
+          __syncwarp();
+        }
+        if (p.C) {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            *reinterpret_cast<float4*>(&stg[lane * 32 + ((c4 ^ (lane & 7)) << 2)]) =
+                make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + (lane >> 3), c4 = lane & 7;
+            const float4 v = *reinterpret_cast<const float4*>(&stg[rl * 32 + ((c4 ^ (rl & 7)) << 2)]);
+            if (row0 + rl < p.M) *reinterpret_cast<float4*>(p.C + (long long)(row0 + rl) * p.ldc + nbase + c4 * 4) = v;
+          }
+          __syncwarp();
+        }
+        if (p.O.hi) {
+          // split to bf16 hi/lo; staging: plane [32 rows][4 chunks of 16 B], chunk slot swizzled by (row>>1)&3
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            __nv_bfloat16 h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ptx::split_bf16(acc[cc * 8 + e], h[e], l[e]);
+            const int slot = (lane * 4 + (cc ^ ((lane >> 1) & 3))) * 16;
+            *reinterpret_cast<uint4*>(stgb + slot) =
+                make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
+            *reinterpret_cast<uint4*>(stgb + 2048 + slot) =
+                make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+          }
+          __syncwarp();
+          const int kb_out = p.o_kb0 + (nbase >> 6);
+          const size_t toff = ((size_t)mt * p.O.kblocks + kb_out) * IMG_TILE_ELEMS;
+          uint8_t* ohi = reinterpret_cast<uint8_t*>(p.O.hi + toff);
+          uint8_t* olo = reinterpret_cast<uint8_t*>(p.O.lo + toff);
+          const int gch0 = (nbase & 63) >> 3;   // first 16-byte chunk of these 32 columns inside the 64-wide k-block
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = i * 8 + (lane >> 2), cc = lane & 3;
+            const int r_in = q * 32 + rl;
+            const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
+            const uint4 vh = *reinterpret_cast<const uint4*>(stgb + slot);
+            const uint4 vl = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
+            if (row0 + rl < p.M) {
+              const uint32_t off = ptx::sw128_offset(r_in, (gch0 + cc) * 8);
+              *reinterpret_cast<uint4*>(ohi + off) = vh;
+              *reinterpret_cast<uint4*>(olo + off) = vl;
             }
           }
+          __syncwarp();
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
+      if (tl < 4 && warp == 2 && lane == 0) LTR_STAMP(tl * 16 + 5);
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
     }
   }

@@ -745,4 +745,49 @@ int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float
   return LTR_OK;
 }
 
+// Micro-benchmark of the image GEMM engine: average device ms per launch of an [m,k]x[n,k]^T
+// problem with zero-filled operands (timing only).  out_mode: 0 fp32 rows, 1 image, 2 both.
+static unsigned long long g_trace_host[64];
+const unsigned long long* ltr_gemm_trace(void) { return g_trace_host; }
+
+float ltr_gemm_bench(int32_t m, int32_t n, int32_t k, int32_t bn_hint, int32_t out_mode, int32_t iters, int32_t device) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.f;
+  const size_t mpad = (size_t)cdiv(m, 128) * 128;
+  uint16_t *dw = nullptr, *da = nullptr, *dout = nullptr;
+  float* dc = nullptr;
+  cudaMalloc(&dw, 2 * (size_t)n * k * 2);
+  cudaMalloc(&da, 2 * mpad * k * 2);
+  cudaMalloc(&dout, 2 * mpad * n * 2);
+  cudaMalloc(&dc, mpad * n * 4);
+  cudaMemset(dw, 0, 2 * (size_t)n * k * 2);
+  cudaMemset(da, 0, 2 * mpad * k * 2);
+  GemmImgArgs a{};
+  a.A = ActImg{reinterpret_cast<__nv_bfloat16*>(da), reinterpret_cast<__nv_bfloat16*>(da + mpad * k), k / 64};
+  a.W.hi = reinterpret_cast<const __nv_bfloat16*>(dw);
+  a.W.lo = reinterpret_cast<const __nv_bfloat16*>(dw + (size_t)n * k);
+  a.W.N = n; a.W.K = k; a.M = m; a.act = 1;
+  if (out_mode == 0 || out_mode == 2) { a.C = dc; a.ldc = n; }
+  if (out_mode == 1 || out_mode == 2) a.O = ActImg{reinterpret_cast<__nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dout + mpad * n), n / 64};
+  unsigned long long* dtrace = nullptr;
+  cudaMalloc(&dtrace, 64 * 8);
+  cudaMemset(dtrace, 0, 64 * 8);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) launch_gemm_img(a, 0, bn_hint);
+  a.trace = dtrace;
+  launch_gemm_img(a, 0, bn_hint);
+  a.trace = nullptr;
+  cudaMemcpy(g_trace_host, dtrace, 64 * 8, cudaMemcpyDeviceToHost);
+  cudaFree(dtrace);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < iters; ++i) launch_gemm_img(a, 0, bn_hint);
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dw); cudaFree(da); cudaFree(dout); cudaFree(dc);
+  return cudaGetLastError() == cudaSuccess ? ms / iters : -1.f;
+}
+
 }  // extern "C"
