@@ -202,6 +202,11 @@ float ltr_gemm_bench(int32_t m, int32_t n, int32_t k, int32_t bn_hint, int32_t o
  * TMEM chunk read, 5 epilogue done, 6 producer slot free).  Debug aid. */
 const unsigned long long* ltr_gemm_trace(void);
 
+/* Debug tracing: kernels instrumented with LTR_DBG_STAMP store clock64 stamps of their first
+ * CTA into a 128-slot device array while tracing is armed. */
+void ltr_debug_trace_arm(int32_t on);
+int ltr_debug_trace_read(unsigned long long* out128);
+
 /* Instrumentation.  Kernel launches issued by this library since the last reset. */
 int64_t ltr_launch_count(void);
 void ltr_reset_launch_count(void);

@@ -21,7 +21,7 @@ LAYOUT_CHANNEL_FIRST = 1
 # Every symbol include/linetr_b200.h declares (tests check the library exports all of them).
 EXPORTED_SYMBOLS = (
     "ltr_abi_version", "ltr_last_error", "ltr_create", "ltr_destroy", "ltr_encode_workspace_bytes",
-    "ltr_encode", "ltr_match", "ltr_match_distmat", "ltr_merge_sublines", "ltr_linear", "ltr_linear_tc", "ltr_linear_img", "ltr_gemm_bench", "ltr_gemm_trace", "ltr_launch_count",
+    "ltr_encode", "ltr_match", "ltr_match_distmat", "ltr_merge_sublines", "ltr_linear", "ltr_linear_tc", "ltr_linear_img", "ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read", "ltr_launch_count",
     "ltr_reset_launch_count", "ltr_profile_begin", "ltr_profile_end",
 )
 
@@ -109,6 +109,10 @@ def load():
     lib.ltr_gemm_bench.argtypes = [C.c_int32] * 7
     lib.ltr_gemm_bench.restype = C.c_float
     lib.ltr_gemm_trace.restype = C.POINTER(C.c_uint64)
+    lib.ltr_debug_trace_arm.argtypes = [C.c_int32]
+    lib.ltr_debug_trace_arm.restype = None
+    lib.ltr_debug_trace_read.argtypes = [C.POINTER(C.c_uint64)]
+    lib.ltr_debug_trace_read.restype = C.c_int
     lib.ltr_launch_count.restype = C.c_int64
     lib.ltr_reset_launch_count.restype = None
     lib.ltr_profile_begin.restype = None

@@ -69,6 +69,14 @@ struct LaunchScope {
   }
 };
 
+// ---------------------------------------------------------------- debug tracing (clock64 stamps of CTA 0)
+__device__ unsigned long long g_dbg_trace[128];
+__device__ int g_dbg_on = 0;
+#define LTR_DBG_STAMP(slot)                                            \
+  do {                                                                 \
+    if (g_dbg_on && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg_trace[slot] = clock64(); \
+  } while (0)
+
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -747,6 +747,20 @@ int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float
 
 // Micro-benchmark of the image GEMM engine: average device ms per launch of an [m,k]x[n,k]^T
 // problem with zero-filled operands (timing only).  out_mode: 0 fp32 rows, 1 image, 2 both.
+// debug: arm / read the clock64 stamps kernels of CTA 0 leave in g_dbg_trace (see LTR_DBG_STAMP)
+void ltr_debug_trace_arm(int32_t on) {
+  int v = on;
+  cudaMemcpyToSymbol(g_dbg_on, &v, sizeof(int));
+  if (on) {
+    static unsigned long long zeros[128] = {0};
+    cudaMemcpyToSymbol(g_dbg_trace, zeros, sizeof(zeros));
+  }
+}
+int ltr_debug_trace_read(unsigned long long* out128) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out128, g_dbg_trace, 128 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -2;
+}
+
 static unsigned long long g_trace_host[64];
 const unsigned long long* ltr_gemm_trace(void) { return g_trace_host; }
 

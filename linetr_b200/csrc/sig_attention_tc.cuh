@@ -2,11 +2,12 @@
 // image, per head, no mask (attention(), models/line_transformer.py:132-136; 1/8 is folded into
 // W_q and the heads are head-major, see ltr_create).
 //
-// CTA = (128-query tile, head, image), 128 threads, thread t <-> query row t <-> TMEM lane t.
-// Per key tile of 128 lines:
-//   * q, k, v fp32 rows are gathered from the qkv buffer, split into bf16 hi/lo and written as
-//     K-major SWIZZLE_128B operand tiles (v transposed: [64 dims x 128 keys]); images are not
-//     tile aligned in the row space, hence the CUDA-core gather instead of TMA
+// CTA = (128-query tile, head, image), 256 threads: thread pair <-> query row (TMEM lane), the two
+// threads of a pair own the two halves of the columns.  Per key tile of 128 lines:
+//   * q, k, v fp32 rows are gathered (coalesced, all loads in flight at once) from the qkv buffer,
+//     split into bf16 hi/lo and written as SWIZZLE_128B operand tiles; images are not tile aligned
+//     in the row space, hence the CUDA-core gather instead of TMA.  V is staged exactly like K
+//     ([keys x 64 dims]) and consumed as an MN-major B operand - no transpose anywhere.
 //   * S = Q K^T      tcgen05 (M128 N128 K64, 3 split products), accumulator in TMEM
 //   * p = exp(s - m), row sums in registers; P written as the A operand of the second MMA
 //     (re-using the Q/K shared memory, which is dead once S is complete)
@@ -23,12 +24,13 @@ namespace ltr {
 
 struct SigAttnSmem {
   static constexpr int QK = 64 * 1024;   // Q hi/lo + K hi/lo (4 x 16 KB); later P hi/lo (2 x 32 KB)
-  static constexpr int VT = 32 * 1024;   // V^T hi/lo: 2 planes x [2 k-blocks][64 d x 64 keys]
-  static constexpr int OFF_BAR = QK + VT;
+  static constexpr int V = 32 * 1024;    // V hi/lo: [128 keys x 64 d] each
+  static constexpr int OFF_RED = QK + V;             // float [2][128] pair reduction scratch
+  static constexpr int OFF_BAR = OFF_RED + 2 * 128 * 4;
   static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
-__global__ void __launch_bounds__(128) sig_attention_tc_kernel(const float* __restrict__ qkv, ActImg out,
+__global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __restrict__ qkv, ActImg out,
                                                                 const int* __restrict__ cu, int lpi) {
   using S = SigAttnSmem;
   int lb, le;
@@ -37,6 +39,9 @@ __global__ void __launch_bounds__(128) sig_attention_tc_kernel(const float* __re
   const int q0 = blockIdx.x * 128;
   if (q0 >= L) return;
   const int h = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qd = warp & 3, half = warp >> 2;
+  const int row = qd * 32 + lane;   // query row of this thread (shared with its pair thread)
+  if (tid == 0) LTR_DBG_STAMP(30);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -47,8 +52,9 @@ __global__ void __launch_bounds__(128) sig_attention_tc_kernel(const float* __re
   uint8_t* k_lo = smem + 49152;
   uint8_t* p_hi = smem;                 // [2 k-blocks][128 x 64 keys]  (aliases q/k)
   uint8_t* p_lo = smem + 32768;
-  uint8_t* vt_hi = smem + S::QK;        // [2 k-blocks][64 d x 64 keys]
-  uint8_t* vt_lo = vt_hi + 16384;
+  uint8_t* v_hi = smem + S::QK;         // [128 keys x 64 d]
+  uint8_t* v_lo = v_hi + 16384;
+  float* red = reinterpret_cast<float*>(smem + S::OFF_RED);
   uint64_t* mma_done = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
 
@@ -66,54 +72,32 @@ __global__ void __launch_bounds__(128) sig_attention_tc_kernel(const float* __re
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t t_s = tmem_base;          // S: 128 columns
   const uint32_t t_o = tmem_base + 128;    // O: 64 columns
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
   uint32_t phase = 0;
+  if (tid == 0) LTR_DBG_STAMP(31);
 
-  // gather 64 fp32 of row `grow` (or zeros) -> bf16 hi/lo row `r` of a [128 x 64] operand tile
-  auto stage_row = [&](uint8_t* hi, uint8_t* lo, int r, const float* src, bool live) {
+  // Coalesced gather of a [128 rows x 64] fp32 tile (rows row0.. of the image, column offset col)
+  // into a bf16 hi/lo operand tile.  float4 f = tid + 256 i  ->  row f/16, floats 4*(f%16)..+3.
+  auto load_tile = [&](float4 (&v)[8], int row0, int col) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float v[8];
-      if (live) {
-        const float4 a = *reinterpret_cast<const float4*>(src + c * 8);
-        const float4 b = *reinterpret_cast<const float4*>(src + c * 8 + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      }
-      __nv_bfloat16 hh[8], ll[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) ptx::split_bf16(v[e], hh[e], ll[e]);
-      const uint32_t off = ptx::sw128_offset(r, c * 8);
-      *reinterpret_cast<uint4*>(hi + off) =
-          make_uint4(ptx::pack_bf16(hh[0], hh[1]), ptx::pack_bf16(hh[2], hh[3]), ptx::pack_bf16(hh[4], hh[5]), ptx::pack_bf16(hh[6], hh[7]));
-      *reinterpret_cast<uint4*>(lo + off) =
-          make_uint4(ptx::pack_bf16(ll[0], ll[1]), ptx::pack_bf16(ll[2], ll[3]), ptx::pack_bf16(ll[4], ll[5]), ptx::pack_bf16(ll[6], ll[7]));
+    for (int i = 0; i < 8; ++i) {
+      const int f = tid + 256 * i, r = f >> 4, c4 = f & 15;
+      v[i] = (row0 + r < L) ? __ldg(reinterpret_cast<const float4*>(qkv + (long long)(lb + row0 + r) * 768 + col + h * 64 + c4 * 4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  auto stage_qk = [&](int k0) {
-    const bool ql = q0 + tid < L, kl = k0 + tid < L;
-    stage_row(q_hi, q_lo, tid, qkv + (long long)(lb + q0 + tid) * 768 + h * 64, ql);
-    stage_row(k_hi, k_lo, tid, qkv + (long long)(lb + k0 + tid) * 768 + 256 + h * 64, kl);
-  };
-  auto stage_vt = [&](int k0) {   // thread = key j: V^T[d][j]
-    const bool kl = k0 + tid < L;
-    const float* src = qkv + (long long)(lb + k0 + tid) * 768 + 512 + h * 64;
-    const uint32_t kb_off = (tid >> 6) * 8192;
+  auto store_tile = [&](const float4 (&v)[8], uint8_t* hi, uint8_t* lo) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kl) a = *reinterpret_cast<const float4*>(src + c * 4);
-      const float v[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __nv_bfloat16 hh, ll;
-        ptx::split_bf16(v[e], hh, ll);
-        const uint32_t off = kb_off + ptx::sw128_offset(c * 4 + e, tid & 63);
-        *reinterpret_cast<__nv_bfloat16*>(vt_hi + off) = hh;
-        *reinterpret_cast<__nv_bfloat16*>(vt_lo + off) = ll;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const int f = tid + 256 * i, r = f >> 4, c4 = f & 15;
+      __nv_bfloat16 hh[4], ll[4];
+      ptx::split_bf16(v[i].x, hh[0], ll[0]);
+      ptx::split_bf16(v[i].y, hh[1], ll[1]);
+      ptx::split_bf16(v[i].z, hh[2], ll[2]);
+      ptx::split_bf16(v[i].w, hh[3], ll[3]);
+      const uint32_t off = ptx::sw128_offset(r, c4 * 4);
+      *reinterpret_cast<uint2*>(hi + off) = make_uint2(ptx::pack_bf16(hh[0], hh[1]), ptx::pack_bf16(hh[2], hh[3]));
+      *reinterpret_cast<uint2*>(lo + off) = make_uint2(ptx::pack_bf16(ll[0], ll[1]), ptx::pack_bf16(ll[2], ll[3]));
     }
   };
   auto issue_s = [&]() {   // S = Q K^T
@@ -133,6 +117,23 @@ __global__ void __launch_bounds__(128) sig_attention_tc_kernel(const float* __re
     ++phase;
     ptx::tc_fence_after();
   };
+  // row maximum over this thread's 64 columns of S, combined with the pair thread through smem
+  auto row_max = [&](int kn, float m_in) {
+    float m = m_in;
+#pragma unroll 1
+    for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+      float s[32];
+      ptx::tmem_ld32(t_s + lane_addr + c0, s);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < kn) m = fmaxf(m, s[j]);
+    }
+    red[half * 128 + row] = m;
+    __syncthreads();
+    m = fmaxf(red[row], red[128 + row]);
+    __syncthreads();
+    return m;
+  };
 
   const int n_kt = (L + 127) / 128;
   float m = -INFINITY;
@@ -140,59 +141,60 @@ __global__ void __launch_bounds__(128) sig_attention_tc_kernel(const float* __re
     // ---- pass 1: row maxima over all key tiles
     for (int kt = 0; kt < n_kt; ++kt) {
       const int k0 = kt * 128, kn = min(128, L - k0);
-      stage_qk(k0);
+      float4 a[8], b[8];
+      load_tile(a, q0, 0);
+      load_tile(b, k0, 256);
+      store_tile(a, q_hi, q_lo);
+      store_tile(b, k_hi, k_lo);
       ptx::fence_proxy_async_smem();
       __syncthreads();
       if (tid == 0) { ptx::tc_fence_after(); issue_s(); }
       wait_mma();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        float s[32];
-        ptx::tmem_ld32(t_s + lane_addr + c0, s);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < kn) m = fmaxf(m, s[j]);
-      }
+      m = row_max(kn, m);
       ptx::tc_fence_before();
       __syncthreads();
     }
   }
   float l = 0.f;
+  constexpr float LOG2E = 1.4426950408889634f;
   for (int kt = 0; kt < n_kt; ++kt) {
     const int k0 = kt * 128, kn = min(128, L - k0);
-    stage_qk(k0);
-    stage_vt(k0);
+    if (tid == 0) LTR_DBG_STAMP(32);
+    {
+      float4 a[8], b[8];
+      load_tile(a, q0, 0);
+      load_tile(b, k0, 256);
+      store_tile(a, q_hi, q_lo);
+      load_tile(a, k0, 512);
+      store_tile(b, k_hi, k_lo);
+      if (tid == 0) LTR_DBG_STAMP(33);
+      store_tile(a, v_hi, v_lo);
+    }
+    if (tid == 0) LTR_DBG_STAMP(34);
     ptx::fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) { ptx::tc_fence_after(); issue_s(); }
     wait_mma();
-    if (n_kt == 1) {
+    if (tid == 0) LTR_DBG_STAMP(35);
+    if (n_kt == 1) m = row_max(kn, m);
+    // p = exp(s - m) -> P operand (q/k shared memory is dead: the S MMAs have completed);
+    // this thread's 64 key columns are exactly k-block `half` of the P tile
+    const float mb = m * LOG2E;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        float s[32];
-        ptx::tmem_ld32(t_s + lane_addr + c0, s);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < kn) m = fmaxf(m, s[j]);
-      }
-    }
-    // p = exp(s - m) -> P operand (q/k shared memory is dead: the S MMAs have completed)
-#pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
       float s[32];
       ptx::tmem_ld32(t_s + lane_addr + c0, s);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        s[j] = (c0 + j < kn) ? expf(s[j] - m) : 0.f;
+        s[j] = (c0 + j < kn) ? exp2f(fmaf(s[j], LOG2E, -mb)) : 0.f;
         l += s[j];
       }
-      const uint32_t kb_off = (c0 >> 6) * 16384;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         __nv_bfloat16 hh[8], ll[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) ptx::split_bf16(s[j + e], hh[e], ll[e]);
-        const uint32_t off = kb_off + ptx::sw128_offset(tid, (c0 & 63) + j);
+        const uint32_t off = half * 16384 + ptx::sw128_offset(row, (c0 & 63) + j);
         *reinterpret_cast<uint4*>(p_hi + off) =
             make_uint4(ptx::pack_bf16(hh[0], hh[1]), ptx::pack_bf16(hh[2], hh[3]), ptx::pack_bf16(hh[4], hh[5]), ptx::pack_bf16(hh[6], hh[7]));
         *reinterpret_cast<uint4*>(p_lo + off) =
@@ -201,44 +203,47 @@ __global__ void __launch_bounds__(128) sig_attention_tc_kernel(const float* __re
     }
     ptx::tc_fence_before();
     ptx::fence_proxy_async_smem();
+    if (tid == 0) LTR_DBG_STAMP(36);
     __syncthreads();
-    if (tid == 0) {   // O += P V
+    if (tid == 0) {   // O += P V    (B = V as an MN-major operand: [K = keys][N = 64 dims])
       ptx::tc_fence_after();
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64);
-      const uint32_t ph = ptx::smem_u32(p_hi), pl = ptx::smem_u32(p_lo), vh = ptx::smem_u32(vt_hi), vl = ptx::smem_u32(vt_lo);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64) | (1u << 16);
+      const uint32_t ph = ptx::smem_u32(p_hi), pl = ptx::smem_u32(p_lo), vh = ptx::smem_u32(v_hi), vl = ptx::smem_u32(v_lo);
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
-          const uint32_t pa = kb * 16384 + k16 * 32, va = kb * 8192 + k16 * 32;
+          const uint32_t pa = kb * 16384 + k16 * 32;          // A: 16 keys = 32 bytes along K
+          const uint32_t va = (kb * 4 + k16) * 2048;          // B: 16 key rows of 128 bytes
           const uint32_t first = (kt | kb | k16) == 0 ? 0u : 1u;
-          ptx::umma_bf16(t_o, ptx::make_sw128_kmajor_desc(pl + pa, 1024), ptx::make_sw128_kmajor_desc(vh + va, 1024), idesc, first);
-          ptx::umma_bf16(t_o, ptx::make_sw128_kmajor_desc(ph + pa, 1024), ptx::make_sw128_kmajor_desc(vl + va, 1024), idesc, 1);
-          ptx::umma_bf16(t_o, ptx::make_sw128_kmajor_desc(ph + pa, 1024), ptx::make_sw128_kmajor_desc(vh + va, 1024), idesc, 1);
+          ptx::umma_bf16(t_o, ptx::make_sw128_kmajor_desc(pl + pa, 1024), ptx::make_sw128_mnmajor_desc(vh + va, 1024, 1024), idesc, first);
+          ptx::umma_bf16(t_o, ptx::make_sw128_kmajor_desc(ph + pa, 1024), ptx::make_sw128_mnmajor_desc(vl + va, 1024, 1024), idesc, 1);
+          ptx::umma_bf16(t_o, ptx::make_sw128_kmajor_desc(ph + pa, 1024), ptx::make_sw128_mnmajor_desc(vh + va, 1024, 1024), idesc, 1);
         }
       }
       ptx::umma_commit(mma_done);
     }
-    wait_mma();   // P, V^T shared memory may be overwritten by the next key tile
+    wait_mma();   // P, V shared memory may be overwritten by the next key tile
+    if (tid == 0) LTR_DBG_STAMP(37);
   }
-  // ---- epilogue: o / l -> image
+  // ---- epilogue: o / l -> image (this thread: 32 of the 64 head dims)
   {
-    const float inv = 1.f / l;
-    const bool live = q0 + tid < L;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      float o[32];
-      ptx::tmem_ld32(t_o + lane_addr + c0, o);
-      if (live) {
+    red[half * 128 + row] = l;
+    __syncthreads();
+    const float inv = 1.f / (red[row] + red[128 + row]);
+    const bool live = q0 + row < L;
+    float o[32];
+    ptx::tmem_ld32(t_o + lane_addr + half * 32, o);
+    if (live) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const float v[8] = {o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv,
-                              o[j + 4] * inv, o[j + 5] * inv, o[j + 6] * inv, o[j + 7] * inv};
-          img_store8(out, lb + q0 + tid, h * 64 + c0 + j, v);
-        }
+      for (int j = 0; j < 32; j += 8) {
+        const float v[8] = {o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv,
+                            o[j + 4] * inv, o[j + 5] * inv, o[j + 6] * inv, o[j + 7] * inv};
+        img_store8(out, lb + q0 + row, h * 64 + half * 32 + j, v);
       }
     }
   }
+  if (tid == 0) LTR_DBG_STAMP(38);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
@@ -254,7 +259,7 @@ inline int launch_sig_attention_tc(const float* qkv, ActImg out, const int* cu, 
   }
   dim3 grid(cdiv(max_l, 128), 4, n_images);
   LaunchScope ls(KC_SIG_ATTN, s);
-  sig_attention_tc_kernel<<<grid, 128, SigAttnSmem::TOTAL, s>>>(qkv, out, cu, lpi);
+  sig_attention_tc_kernel<<<grid, 256, SigAttnSmem::TOTAL, s>>>(qkv, out, cu, lpi);
   LTR_CUDA_TRY(cudaGetLastError());
   return 0;
 }

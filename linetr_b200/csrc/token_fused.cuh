@@ -130,6 +130,14 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
         ++it;
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        {   // pull the NEXT tile's descriptors (the mandatory HBM read of this stage) into L2
+          const long long nt = (long long)(tile + gridDim.x) * p.lpt * p.T;
+          const long long total = (long long)p.R * p.T;
+          if (nt < total) {
+            const long long rows = min((long long)p.lpt * p.T, total - nt);
+            ptx::bulk_prefetch_l2(p.desc + nt * 256, (uint32_t)(rows * 1024));
+          }
+        }
         push(p.W3, 0, 0);
         for (int nb = 0; nb < 2; ++nb)
           for (int kb = 0; kb < 2; ++kb) push(p.W4, nb, kb);
@@ -208,6 +216,8 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       const long long tok0 = (long long)line0 * p.T;
       const long long n_tok_total = (long long)p.R * p.T;
       const bool row_live = r_in < rows_used && tok0 + r_in < n_tok_total;
+      const bool tr = (tile == blockIdx.x + gridDim.x) && warp == 2 && lane == 0;   // trace the CTA's 2nd tile
+      if (tr) LTR_DBG_STAMP(0);
       // ---- P0: 3 -> 32 -> 64 for this row, this thread produces outputs [32*half, 32*half+32)
       {
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;
@@ -241,9 +251,11 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(a_ready);
+      if (tr) LTR_DBG_STAMP(1);
       // ---- epilogue L3: 128 columns (64 per half) -> h128
       ptx::mbar_wait(acc_ready, nacc++ & 1);
       ptx::tc_fence_after();
+      if (tr) LTR_DBG_STAMP(2);
 #pragma unroll 1
       for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         float acc[32];
@@ -259,9 +271,11 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(a_ready);
+      if (tr) LTR_DBG_STAMP(3);
       // ---- epilogue L4: 256 columns (128 per half) -> h256
       ptx::mbar_wait(acc_ready, nacc++ & 1);
       ptx::tc_fence_after();
+      if (tr) LTR_DBG_STAMP(4);
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         float acc[32];
@@ -277,13 +291,34 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(a_ready);
+      if (tr) LTR_DBG_STAMP(5);
       // ---- epilogue L5: x = acc + b5 + desc -> fp32 tile in the (now dead) activation region,
       //      partial CLS scores over this thread's 128 columns
       ptx::mbar_wait(acc_ready, nacc++ & 1);
       ptx::tc_fence_after();
+      if (tr) LTR_DBG_STAMP(6);
       float* xs = reinterpret_cast<float*>(act);
+      {   // phase A: the tile's descriptors are ONE contiguous 128 KB range: coalesced copy into the
+          // (now dead) activation region, in the swizzled x layout
+        const float4* dsrc = reinterpret_cast<const float4*>(p.desc + tok0 * 256);
+        const long long rows_avail = n_tok_total - tok0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          float4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int f = wt + 256 * (i0 + i), r = f >> 6;
+            v[i] = (r < rows_used && r < rows_avail) ? __ldg(dsrc + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int f = wt + 256 * (i0 + i), r = f >> 6, c4 = f & 63;
+            *reinterpret_cast<float4*>(&xs[xs_index(r, c4 * 4)]) = v[i];
+          }
+        }
+      }
+      worker_sync();
       float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
-      const float* drow = p.desc + (tok0 + r_in) * 256;
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         float acc[32];
@@ -291,14 +326,14 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const int n = c0 + j;
-          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_live) d = __ldg(reinterpret_cast<const float4*>(drow + n));
+          float4* xp = reinterpret_cast<float4*>(&xs[xs_index(r_in, n)]);
+          const float4 d = *xp;
           float4 x;
           x.x = acc[j] + sB5[n] + d.x;
           x.y = acc[j + 1] + sB5[n + 1] + d.y;
           x.z = acc[j + 2] + sB5[n + 2] + d.z;
           x.w = acc[j + 3] + sB5[n + 3] + d.w;
-          *reinterpret_cast<float4*>(&xs[xs_index(r_in, n)]) = x;
+          *xp = x;
           const float4 u0 = *reinterpret_cast<const float4*>(&sU[n]);
           const float4 u1 = *reinterpret_cast<const float4*>(&sU[256 + n]);
           const float4 u2 = *reinterpret_cast<const float4*>(&sU[512 + n]);
@@ -311,7 +346,9 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       }
       ptx::tc_fence_before();
       *reinterpret_cast<float4*>(&sSc[(half * 128 + r_in) * 4]) = make_float4(sc0, sc1, sc2, sc3);
+      if (tr) LTR_DBG_STAMP(7);
       worker_sync();
+      if (tr) LTR_DBG_STAMP(8);
       // ---- softmax over the T tokens + CLS of every (line, head): threads 0 .. 4*lpt-1
       for (int pi = wt; pi < 4 * p.lpt; pi += 256) {
         const int ln = pi >> 2, h = pi & 3;
@@ -329,6 +366,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
         sP[(128 + ln) * 4 + h] = e0 * inv;
       }
       worker_sync();
+      if (tr) LTR_DBG_STAMP(9);
       // ---- pooling: thread = channel; z_h[c] = p_cls * cls[c] + sum_n p[n] x[n][c]
       {
         const int c = wt;
@@ -351,7 +389,9 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
           img_store1(p.z, gl, 768 + c, z3);
         }
       }
+      if (tr) LTR_DBG_STAMP(10);
       worker_sync();   // x tile and probabilities are dead: the next tile may overwrite them
+      if (tr) LTR_DBG_STAMP(11);
     }
   }
   ptx::tc_fence_before();

@@ -368,3 +368,43 @@ def test_full_size_properties(L, T, P):
         ok = m >= 0
         assert ok.sum() >= 0.9 * L
         assert np.array_equal(perms[p][m[ok]], np.nonzero(ok)[0])
+
+
+def test_cfg3_ragged_stress_vs_oracle():
+    """BASELINE cfg[3] shape class: ragged 32..512 lines per image, 64 tokens per line (ragged mask),
+    several pairs per call.  Descriptors of the smallest/largest images vs the oracle, matches of
+    every pair recover the known permutation."""
+    model, sd = model_for("synthetic:0:1")
+    eng = engine.PairEngine(model, DEV)
+    rng = np.random.Generator(np.random.PCG64(33))
+    Ls = [32, 512, int(rng.integers(33, 512)), int(rng.integers(33, 512))]
+    pairs, perms = [], []
+    for p, L in enumerate(Ls):
+        a, b, perm = syn.make_pair_inputs(600 + p, L, 64, n_real_tokens=(5, 64))
+        pairs.append((a, b))
+        perms.append(perm)
+    batch = engine.LineBatch.from_images([a for a, _ in pairs] + [b for _, b in pairs]).to(DEV)
+    res = eng.match_packed(batch, len(Ls), 0.8, keep_desc=True)
+    d0 = res.desc0.cpu().numpy()
+    for p in (0, 1):   # L = 32 and L = 512 (4 key tiles in the attention kernel)
+        s, e = batch.cu_lines[p], batch.cu_lines[p + 1]
+        want = orc.line_transformer_forward(sd, pairs[p][0])[0]
+        assert np.abs(d0[s:e].T - want).max() < DESC_TOL_TIGHT
+    for p, L in enumerate(Ls):
+        m = res.pair(p).cpu().numpy()
+        ok = m >= 0
+        assert ok.sum() >= 0.9 * L and np.array_equal(perms[p][m[ok]], np.nonzero(ok)[0])
+        assert int(res.counts[p]) == int(ok.sum())
+
+
+def test_cfg4_matcher_only_1024_exact():
+    """BASELINE cfg[4]: matcher only, 1024 x 1024 x d256.  Indices identical to the oracle
+    (numpy fp32 BLAS distance + argmin) and to the known permutation."""
+    d0, d1, perm = syn.make_descriptor_pair(71, 1024, 1024)
+    mat, dist = nnm.nn_matcher(d0, d1, 0.8, True)
+    want, wdist = orc.nn_matcher(d0, d1, 0.8, True)
+    assert np.array_equal(mat, want)
+    assert np.abs(dist - wdist).max() < 5e-6
+    idx = orc.match_indices(mat)
+    ok = idx >= 0
+    assert ok.sum() >= 1000 and np.array_equal(perm[idx[ok]], np.nonzero(ok)[0])

@@ -1,0 +1,29 @@
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from linetr_b200 import LineBatch, LineTransformer, PairEngine, _native as N, synthetic as syn
+lib = N.load()
+dev = torch.device("cuda", 0)
+sd = syn.make_state_dict(0, 1)
+m = LineTransformer({"mode": "train"}); m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m = m.eval().to(dev)
+eng = PairEngine(m, dev)
+ims = [syn.make_image_inputs(i, 128, 21) for i in range(64)]
+b = LineBatch.from_images(ims).to(dev)
+eng.encode(b); torch.cuda.synchronize()
+lib.ltr_debug_trace_arm(1)
+eng.encode(b); torch.cuda.synchronize()
+buf = (C.c_uint64 * 128)()
+lib.ltr_debug_trace_read(buf)
+lib.ltr_debug_trace_arm(0)
+v = [buf[i] for i in range(12)]
+a = [buf[i] for i in range(30, 39)]
+names = ["P0 start", "P0 done", "L3 acc", "ep3 done", "L4 acc", "ep4 done", "L5 acc", "ep5 done", "sync", "softmax done", "pool done", "tile end"]
+for i in range(1, 12):
+    print(f"{names[i]:14s} +{v[i]-v[i-1]:7d} cycles")
+print("tile total", v[11] - v[0])
+
+an = ["start", "tmem alloc+sync", "kt start", "stage q,k", "stage v^T", "S mma done", "softmax+P stored", "PV mma done", "epilogue done"]
+print("attention CTA (0,0,0), last layer:")
+for i in range(1, 9):
+    print(f"{an[i]:18s} +{a[i]-a[i-1]:7d} cycles")
+print("attention CTA total", a[8] - a[0])
