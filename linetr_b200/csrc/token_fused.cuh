@@ -211,6 +211,52 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       *reinterpret_cast<uint4*>(act + nkb * 16384 + off) =
           make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
     };
+    // P0: narrow MLP 3 -> 32 -> 64 (+ReLU) for this thread's token row of tile `t`; the thread produces
+    // outputs [32*half, 32*half+32) and keeps them as packed split-bf16 registers until p0_store().
+    uint32_t p0_hi[16], p0_lo[16];
+    auto p0_compute = [&](int t) {
+      const long long tk0 = (long long)t * p.lpt * p.T;
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+      if (r_in < rows_used && tk0 + r_in < (long long)p.R * p.T) {
+        const long long tk = tk0 + r_in;
+        x0 = (p.pnt[2 * tk] - p.cx) / p.scale;
+        x1 = (p.pnt[2 * tk + 1] - p.cy) / p.scale;
+        x2 = p.score[tk];
+      }
+      float h1[32];
+#pragma unroll
+      for (int n = 0; n < 32; ++n)
+        h1[n] = fmaxf(fmaf(sW1[n * 3 + 2], x2, fmaf(sW1[n * 3 + 1], x1, fmaf(sW1[n * 3], x0, sB1[n]))), 0.f);
+#pragma unroll
+      for (int n0 = 0; n0 < 32; n0 += 2) {
+        float o[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int n = half * 32 + n0 + j;
+          float a = sB2[n];
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(&sW2[n * 32 + k]);
+            a = fmaf(w.x, h1[k], a); a = fmaf(w.y, h1[k + 1], a);
+            a = fmaf(w.z, h1[k + 2], a); a = fmaf(w.w, h1[k + 3], a);
+          }
+          o[j] = fmaxf(a, 0.f);
+        }
+        __nv_bfloat16 h0, l0, h1b, l1b;
+        ptx::split_bf16(o[0], h0, l0);
+        ptx::split_bf16(o[1], h1b, l1b);
+        p0_hi[n0 >> 1] = ptx::pack_bf16(h0, h1b);
+        p0_lo[n0 >> 1] = ptx::pack_bf16(l0, l1b);
+      }
+    };
+    auto p0_store = [&]() {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t off = ptx::sw128_offset(r_in, half * 32 + c * 8);
+        *reinterpret_cast<uint4*>(act + off) = make_uint4(p0_hi[c * 4], p0_hi[c * 4 + 1], p0_hi[c * 4 + 2], p0_hi[c * 4 + 3]);
+        *reinterpret_cast<uint4*>(act + 16384 + off) = make_uint4(p0_lo[c * 4], p0_lo[c * 4 + 1], p0_lo[c * 4 + 2], p0_lo[c * 4 + 3]);
+      }
+    };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int line0 = tile * p.lpt;
       const long long tok0 = (long long)line0 * p.T;
@@ -218,37 +264,9 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       const bool row_live = r_in < rows_used && tok0 + r_in < n_tok_total;
       const bool tr = (tile == blockIdx.x + gridDim.x) && warp == 2 && lane == 0;   // trace the CTA's 2nd tile
       if (tr) LTR_DBG_STAMP(0);
-      // ---- P0: 3 -> 32 -> 64 for this row, this thread produces outputs [32*half, 32*half+32)
-      {
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-        if (row_live) {
-          const long long t = tok0 + r_in;
-          x0 = (p.pnt[2 * t] - p.cx) / p.scale;
-          x1 = (p.pnt[2 * t + 1] - p.cy) / p.scale;
-          x2 = p.score[t];
-        }
-        float h1[32];
-#pragma unroll
-        for (int n = 0; n < 32; ++n)
-          h1[n] = fmaxf(fmaf(sW1[n * 3 + 2], x2, fmaf(sW1[n * 3 + 1], x1, fmaf(sW1[n * 3], x0, sB1[n]))), 0.f);
-#pragma unroll 1
-        for (int n0 = 0; n0 < 32; n0 += 8) {
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int n = half * 32 + n0 + j;
-            float a = sB2[n];
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-              const float4 w = *reinterpret_cast<const float4*>(&sW2[n * 32 + k]);
-              a = fmaf(w.x, h1[k], a); a = fmaf(w.y, h1[k + 1], a);
-              a = fmaf(w.z, h1[k + 2], a); a = fmaf(w.w, h1[k + 3], a);
-            }
-            o[j] = fmaxf(a, 0.f);
-          }
-          act_store8(1, half * 32 + n0, o);
-        }
-      }
+      // ---- P0 result of THIS tile (computed during the previous tile's L5 MMAs) -> h64 operand tile
+      if (tile == (int)blockIdx.x) p0_compute(tile);
+      p0_store();
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(a_ready);
       if (tr) LTR_DBG_STAMP(1);
@@ -292,6 +310,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(a_ready);
       if (tr) LTR_DBG_STAMP(5);
+      if (tile + (int)gridDim.x < p.n_tiles) p0_compute(tile + gridDim.x);   // overlaps the L5 MMAs
       // ---- epilogue L5: x = acc + b5 + desc -> fp32 tile in the (now dead) activation region,
       //      partial CLS scores over this thread's 128 columns
       ptx::mbar_wait(acc_ready, nacc++ & 1);
@@ -302,20 +321,13 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
           // (now dead) activation region, in the swizzled x layout
         const float4* dsrc = reinterpret_cast<const float4*>(p.desc + tok0 * 256);
         const long long rows_avail = n_tok_total - tok0;
-#pragma unroll 1
-        for (int i0 = 0; i0 < 32; i0 += 8) {
-          float4 v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int f = wt + 256 * (i0 + i), r = f >> 6;
-            v[i] = (r < rows_used && r < rows_avail) ? __ldg(dsrc + f) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int f = wt + 256 * (i0 + i), r = f >> 6, c4 = f & 63;
-            *reinterpret_cast<float4*>(&xs[xs_index(r, c4 * 4)]) = v[i];
-          }
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {   // 32 x 16 B per thread, all in flight (cp.async, no registers)
+          const int f = wt + 256 * i, r = f >> 6, c4 = f & 63;
+          const bool ok = r < rows_used && r < rows_avail;
+          ptx::cp_async16(&xs[xs_index(r, c4 * 4)], ok ? (const void*)(dsrc + f) : (const void*)p.desc, ok ? 16u : 0u);
         }
+        ptx::cp_async_wait_all();
       }
       worker_sync();
       float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
