@@ -337,8 +337,7 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   for (size_t li = 0; li < m->sig.size(); ++li) {
     const SigLayer& L = m->sig[li];
     LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, w.qkv, 768));
-    LTR_TRY(launch_sig_attention_tc(w.qkv, w.o, cu, in.lines_per_image, max_l, in.n_images, s));
-    LTR_TRY(gemm(L.merge, w.o, 0, R, ACT_NONE, s, nullptr, 0, &w.xm, 4));          // message -> xm[:, 256:]
+    LTR_TRY(launch_sig_attention_tc(w.qkv, w.xm, 256, cu, in.lines_per_image, max_l, in.n_images, s));  // o -> xm[:, 256:]
     LTR_TRY(gemm(L.mlp1, w.xm, 0, R, ACT_RELU, s, nullptr, 0, &w.hm, 0));
     LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, w.xf, 256, &w.xm, 0, w.xf, 256));  // x += delta
   }
@@ -513,7 +512,23 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
     if (!fold_layer(tm, p + ".mlp.0", p + ".mlp.1", 2 * D, 2 * D, W1, B1, err) ||
         !fold_layer(tm, p + ".mlp.3", "", D, 2 * D, W2, B2, err))
       return set_error(LTR_E_INVALID, err);
-    so[li] = {hp.add_lin(Wqkv, bqkv, 768, D), hp.add_lin(Wm, vec(bm, D), D, D), hp.add_lin(W1, B1, 2 * D, 2 * D),
+    // Fold the attention output projection (`merge`) into the first MLP layer:
+    //   mlp1([x | merge(o)]) = W1a x + W1b (Wm o + bm) + b1 = [W1a | W1b Wm] [x | o] + (b1 + W1b bm)
+    // so the attention kernel writes o straight into the second half of the MLP input and the
+    // merge GEMM (one launch + one activation round trip per layer) disappears.
+    std::vector<double> W1f((size_t)2 * D * 2 * D), B1f(2 * D);
+    for (int o = 0; o < 2 * D; ++o) {
+      double bacc = B1[o];
+      for (int i = 0; i < D; ++i) W1f[(size_t)o * 2 * D + i] = W1[(size_t)o * 2 * D + i];
+      for (int j = 0; j < D; ++j) {
+        double a = 0.0;
+        for (int i = 0; i < D; ++i) a += W1[(size_t)o * 2 * D + D + i] * Wm[(size_t)i * D + j];
+        W1f[(size_t)o * 2 * D + D + j] = a;
+      }
+      for (int i = 0; i < D; ++i) bacc += W1[(size_t)o * 2 * D + D + i] * (double)bm[i];
+      B1f[o] = bacc;
+    }
+    so[li] = {hp.add_lin(Wqkv, bqkv, 768, D), hp.add_lin(Wm, vec(bm, D), D, D), hp.add_lin(W1f, B1f, 2 * D, 2 * D),
               hp.add_lin(W2, B2, D, 2 * D)};
   }
   std::vector<double> Wf, Bf;

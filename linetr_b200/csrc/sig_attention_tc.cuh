@@ -14,7 +14,8 @@
 //   * O += P V       tcgen05 (M128 N64 K128), accumulated in TMEM across key tiles
 // Images with more than 128 lines run a first pass that only computes the row maxima (S is
 // recomputed in the second pass - QK^T is 1/3 of the work and far from the bottleneck), so no
-// rescaling of the TMEM accumulator is ever needed.  Output: split-bf16 activation image [R, 256].
+// rescaling of the TMEM accumulator is ever needed.  Output: columns [out_k0, out_k0+256) of a split-bf16
+// activation image (the second half of the signature MLP input; the `merge` projection is folded into W1).
 #pragma once
 #include "act_img.cuh"
 #include "common.cuh"
@@ -30,7 +31,7 @@ struct SigAttnSmem {
   static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
-__global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __restrict__ qkv, ActImg out,
+__global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __restrict__ qkv, ActImg out, int out_k0,
                                                                 const int* __restrict__ cu, int lpi) {
   using S = SigAttnSmem;
   int lb, le;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
       for (int j = 0; j < 32; j += 8) {
         const float v[8] = {o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv,
                             o[j + 4] * inv, o[j + 5] * inv, o[j + 6] * inv, o[j + 7] * inv};
-        img_store8(out, lb + q0 + row, h * 64 + half * 32 + j, v);
+        img_store8(out, lb + q0 + row, out_k0 + h * 64 + half * 32 + j, v);
       }
     }
   }
@@ -249,8 +250,8 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
   if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
 }
 
-inline int launch_sig_attention_tc(const float* qkv, ActImg out, const int* cu, int lpi, int max_l, int n_images,
-                                   cudaStream_t s) {
+inline int launch_sig_attention_tc(const float* qkv, ActImg out, int out_k0, const int* cu, int lpi, int max_l,
+                                   int n_images, cudaStream_t s) {
   if (max_l <= 0 || n_images <= 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -259,7 +260,7 @@ inline int launch_sig_attention_tc(const float* qkv, ActImg out, const int* cu, 
   }
   dim3 grid(cdiv(max_l, 128), 4, n_images);
   LaunchScope ls(KC_SIG_ATTN, s);
-  sig_attention_tc_kernel<<<grid, 256, SigAttnSmem::TOTAL, s>>>(qkv, out, cu, lpi);
+  sig_attention_tc_kernel<<<grid, 256, SigAttnSmem::TOTAL, s>>>(qkv, out, out_k0, cu, lpi);
   LTR_CUDA_TRY(cudaGetLastError());
   return 0;
 }
