@@ -24,6 +24,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "image-pairs/s (line-descriptor forward x2 + mutual-NN match)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class from the
+# committed `ncu --set full` capture (profiles/), bytes; None until a capture exists
+TRAFFIC_NCU = {"linear": 38.7e6}   # profiles/r1_final_kernels.md (prof_v6), average over one signature layer
 UNIT = "pairs/s"
 
 
@@ -54,12 +57,19 @@ def flops_per_image(L, T, n_sig=7):
 
 
 def gemm_flops_per_image(L, T, n_sig=7):
-    """FLOPs executed by the `linear` kernel class (wide layers only) for one image."""
-    tok = 2 * (128 * 256 + 256 * 256) * L * T
+    """Useful FLOPs the `linear` kernel class (gemm_img_kernel launches) is responsible for, one
+    image: line stage (per-head V projection, fc, FFN, wide line-positional layers), signature
+    layers (qkv, MLP with the merge projection folded in, MLP out) and final_proj.  The 3x
+    split-bf16 products and the zero blocks of the block-diagonal V projection are NOT counted."""
     line = 2 * (4 * 256 * 64 + 256 * 256 + 2 * 256 * 1024 + 128 * 256 + 256 * 256) * L
-    sig = 2 * (256 * 768 + 256 * 256 + 512 * 512 + 512 * 256) * L * n_sig
+    sig = 2 * (256 * 768 + 512 * 512 + 512 * 256) * L * n_sig
     fin = 2 * 256 * 256 * L
-    return tok + line + sig + fin
+    return line + sig + fin
+
+
+def token_flops_per_image(L, T):
+    """Useful FLOPs of token_fused_kernel: narrow MLP 3-32-64, 64-128-256-256 on tensor cores, CLS pooling."""
+    return (2 * (3 * 32 + 32 * 64 + 64 * 128 + 128 * 256 + 256 * 256) + 4096) * L * T
 
 
 def bytes_per_image(L, T):
@@ -267,17 +277,21 @@ def main():
         dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 0))
         dom_name, (dom_ms, dom_launches) = dom
         shares = {k: round(v[0] / max(sum(x[0] for x in prof.values()), 1e-9), 4) for k, v in prof.items()}
-        gemm_flops_step = 2 * P * gemm_flops_per_image(L, T)
+        class_flops = {"linear": 2 * P * gemm_flops_per_image(L, T), "token_fused": 2 * P * token_flops_per_image(L, T),
+                       "sig_attention": 2 * P * 7 * 1024 * L * L}
+        class_kernel = {"linear": "gemm_img_kernel (tcgen05, split-bf16 x3, TMA-fed tile images)",
+                        "token_fused": "token_fused_kernel (tcgen05 + CUDA-core pooling)",
+                        "sig_attention": "sig_attention_tc_kernel (tcgen05)"}
         useful_flops_step = 2 * P * flops_per_image(L, T) + P * 512 * L * L
         roof = None
-        if dom_name == "linear" and dom_launches:
-            per_launch_flops = gemm_flops_step * args.steps / dom_launches
+        if dom_name in class_flops and dom_launches:
+            per_launch_flops = class_flops[dom_name] * args.steps / dom_launches
             avg_ms = dom_ms / dom_launches
             ach = per_launch_flops / (avg_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_img_kernel (tcgen05, split-bf16 x3)", "achieved": ach,
+            roof = {"bound": "tensor", "kernel": class_kernel[dom_name], "achieved": ach,
                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                    "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": TRAFFIC_NCU.get(dom_name),
+                    "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json); useful FLOPs only",
                     "launches_per_step": dom_launches / args.steps, "avg_launch_ms": avg_ms,
                     "algorithmic_flops_per_launch": per_launch_flops}
         cpu_v, cpu_n, cores, note = cpu_reference_pairs_per_s(L, T, args.cpu_budget)

@@ -175,14 +175,8 @@ int ltr_linear(const float* x, int32_t ldx, const float* w, const float* bias, c
                int32_t ldr, float* y, int32_t ldy, int32_t m, int32_t n, int32_t k, int32_t act,
                int32_t device, void* stream);
 
-/* The same on the tensor-core engine (tcgen05, split-bf16 operands).  `w_host` is a HOST
- * pointer to the fp32 [n, k] weights: it is packed, uploaded, used and freed inside the call
- * (synchronous; unit-test hook only).  n and k must be multiples of 64. */
-int ltr_linear_tc(const float* x, int32_t ldx, const float* w_host, const float* bias,
-                  const float* res, int32_t ldr, float* y, int32_t ldy, int32_t m, int32_t n,
-                  int32_t k, int32_t act, int32_t device, void* stream);
-
-/* The same on the persistent image-operand engine (gemm_img.cuh): x is converted to a
+/* The same on the tensor-core engine (gemm_img.cuh: persistent, TMA-fed split-bf16 tile images,
+ * tcgen05): x is converted to a
  * split-bf16 tile image, the GEMM writes fp32 rows into `y` (may be NULL) and - when
  * `y_from_image` is given - also the split-bf16 image of the result, which is converted back
  * to fp32 rows [m, n] there so that both outputs can be checked.  n % 128 == 0, k % 64 == 0;

@@ -21,7 +21,7 @@ LAYOUT_CHANNEL_FIRST = 1
 # Every symbol include/linetr_b200.h declares (tests check the library exports all of them).
 EXPORTED_SYMBOLS = (
     "ltr_abi_version", "ltr_last_error", "ltr_create", "ltr_destroy", "ltr_encode_workspace_bytes",
-    "ltr_encode", "ltr_match", "ltr_match_distmat", "ltr_merge_sublines", "ltr_linear", "ltr_linear_tc", "ltr_linear_img", "ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read", "ltr_launch_count",
+    "ltr_encode", "ltr_match", "ltr_match_distmat", "ltr_merge_sublines", "ltr_linear", "ltr_linear_img", "ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read", "ltr_launch_count",
     "ltr_reset_launch_count", "ltr_profile_begin", "ltr_profile_end",
 )
 
@@ -100,8 +100,6 @@ def load():
     lib.ltr_linear.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.ltr_linear.restype = C.c_int
-    lib.ltr_linear_tc.argtypes = lib.ltr_linear.argtypes
-    lib.ltr_linear_tc.restype = C.c_int
     lib.ltr_linear_img.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p]

@@ -194,21 +194,19 @@ def match_distmat(dist: torch.Tensor, nn_thresh: float, mutual=True):
     return out
 
 
-def linear(x: torch.Tensor, w: torch.Tensor, bias=None, res=None, act=0, engine="f32") -> torch.Tensor:
-    """ltr_linear / ltr_linear_tc: act(x @ w.T + bias) (+ res) on one of the library's GEMM
-    engines (unit-test hook).  engine="tc" takes `w` on the HOST (it is packed per call)."""
+def linear(x: torch.Tensor, w: torch.Tensor, bias=None, res=None, act=0) -> torch.Tensor:
+    """ltr_linear: act(x @ w.T + bias) (+ res) on the fp32 CUDA-core engine (unit-test hook and
+    numerics yardstick of the tensor-core engine)."""
     _req_cuda(x, "x")
-    x = _f32c(x)
-    w = _f32c(w).cpu() if engine == "tc" else _f32c(w)
+    x, w = _f32c(x), _f32c(w)
     M, K = x.shape
     Nn = w.shape[0]
     y = torch.empty((M, Nn), dtype=torch.float32, device=x.device)
     bias = _f32c(bias) if bias is not None else None
     res = _f32c(res) if res is not None else None
     with torch.cuda.device(x.device):
-        fn = N.load().ltr_linear_tc if engine == "tc" else N.load().ltr_linear
-        rc = fn(_ptr(x), K, _ptr(w), _ptr(bias), _ptr(res), Nn, _ptr(y), Nn, M, Nn, K, int(act),
-                x.device.index, _stream_ptr(x.device))
+        rc = N.load().ltr_linear(_ptr(x), K, _ptr(w), _ptr(bias), _ptr(res), Nn, _ptr(y), Nn, M, Nn, K, int(act),
+                                 x.device.index, _stream_ptr(x.device))
     N.check(rc, "ltr_linear")
     return y
 

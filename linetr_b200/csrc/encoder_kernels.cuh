@@ -1,6 +1,5 @@
-// CUDA-core kernels of the line-descriptor forward that are not GEMMs:
-// narrow positional-encoder layers, folded CLS attention pooling, LayerNorm,
-// line-signature attention, final L2 normalisation.
+// CUDA-core kernels of the line-descriptor forward that are not GEMMs: the narrow head of the LINE
+// positional encoder (the token one lives in token_fused.cuh), LayerNorm, final L2 normalisation.
 #pragma once
 #include "act_img.cuh"
 #include "common.cuh"
@@ -154,79 +153,6 @@ small_mlp_kernel(SmallMlpWeights w, const float* __restrict__ in0, const float* 
 }
 
 // ------------------------------------------------------------------------------------
-// Folded CLS-row token attention pooling (models/line_attention.py:13-21,42-75 restricted
-// to query row 0, the only row the reference consumes - models/line_transformer.py:128).
-// The CLS query is a model constant, so q_h . k_h[n] / 8 = x[n] . u_h + const_h with
-// u_h = W_k,h^T q_h / 8; the constant cancels in the softmax.  Output per line and head:
-// z_h = sum_n softmax_n(s_h)[n] * x[n]   (n = 0 is the CLS token itself), which the caller
-// multiplies by W_v,h (sum of probabilities is 1, so the V bias passes through).
-// x: [lines*T, 256] (= desc + word positional encoding); z: image of [lines, 4*256] (row line0 + blockIdx.x).
-constexpr int CP_THREADS = 256;
-constexpr int CP_MAXN = 129;  // T <= 128
-
-__global__ void __launch_bounds__(CP_THREADS)
-cls_pool_kernel(const float* __restrict__ x, const float* __restrict__ U /*[4][256]*/,
-                const float* __restrict__ s_cls /*[4]*/, const float* __restrict__ cls /*[256]*/,
-                ActImg z, int line0, int T) {
-  __shared__ float sc[CP_MAXN][4];
-  const int line = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* __restrict__ xl = x + (long long)line * T * 256;
-  // scores: warp per token, lanes over channels (8 per lane)
-  float4 u[4][2];
-#pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    u[h][0] = *reinterpret_cast<const float4*>(U + h * 256 + lane * 4);
-    u[h][1] = *reinterpret_cast<const float4*>(U + h * 256 + 128 + lane * 4);
-  }
-  for (int n = warp; n < T; n += CP_THREADS / 32) {
-    float4 a = *reinterpret_cast<const float4*>(xl + n * 256 + lane * 4);
-    float4 b = *reinterpret_cast<const float4*>(xl + n * 256 + 128 + lane * 4);
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      float d = a.x * u[h][0].x + a.y * u[h][0].y + a.z * u[h][0].z + a.w * u[h][0].w +
-                b.x * u[h][1].x + b.y * u[h][1].y + b.z * u[h][1].z + b.w * u[h][1].w;
-      d = warp_sum(d);
-      if (lane == 0) sc[n + 1][h] = d;
-    }
-  }
-  if (tid < 4) sc[0][tid] = s_cls[tid];
-  __syncthreads();
-  // softmax over n = 0..T per head: warp h handles head h
-  if (warp < 4) {
-    const int h = warp, N = T + 1;
-    float m = -INFINITY;
-    for (int n = lane; n < N; n += 32) m = fmaxf(m, sc[n][h]);
-    m = warp_max(m);
-    float s = 0.f;
-    for (int n = lane; n < N; n += 32) {
-      float e = expf(sc[n][h] - m);
-      sc[n][h] = e;
-      s += e;
-    }
-    s = warp_sum(s);
-    float inv = 1.f / s;
-    for (int n = lane; n < N; n += 32) sc[n][h] *= inv;
-  }
-  __syncthreads();
-  // pooling: thread = channel
-  const int c = tid;
-  float cv = cls[c];
-  float z0 = sc[0][0] * cv, z1 = sc[0][1] * cv, z2 = sc[0][2] * cv, z3 = sc[0][3] * cv;
-  for (int n = 0; n < T; ++n) {
-    float xv = xl[n * 256 + c];
-    z0 = fmaf(sc[n + 1][0], xv, z0);
-    z1 = fmaf(sc[n + 1][1], xv, z1);
-    z2 = fmaf(sc[n + 1][2], xv, z2);
-    z3 = fmaf(sc[n + 1][3], xv, z3);
-  }
-  const int zr = line0 + line;
-  img_store1(z, zr, c, z0);
-  img_store1(z, zr, 256 + c, z1);
-  img_store1(z, zr, 512 + c, z2);
-  img_store1(z, zr, 768 + c, z3);
-}
-
-// ------------------------------------------------------------------------------------
 // LayerNorm over 256 channels, eps inside the sqrt, biased variance
 // (nn.LayerNorm(d, eps=1e-6), models/line_attention.py:40,83); optional fused add of a
 // second row-major tensor AFTER the normalisation (sentence = klines_pos + enc_out,
@@ -265,101 +191,6 @@ layernorm256_kernel(const float* __restrict__ in, int ldi, const float* __restri
   if (oimg.hi) {
     img_store4(oimg, row, o_k0 + lane * 4, o0.x, o0.y, o0.z, o0.w);
     img_store4(oimg, row, o_k0 + 128 + lane * 4, o1.x, o1.y, o1.z, o1.w);
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// Line-signature attention, one image and head per CTA column: softmax(q k^T / 8) v over
-// the L_i lines of ONE image, no mask (attention(), models/line_transformer.py:132-136).
-// qkv: [n_lines, 768] = [q | k | v], each head-major (c = h*64 + d; the reference's
-// interleaved c = d*4 + h layout is undone when the weights are packed, and 1/8 is folded
-// into W_q).  One thread per query row, keys/values staged through shared memory in
-// tiles of 64, online softmax in chunks of 16 keys.  out: image of [n_lines, 256] head-major.
-constexpr int SA_THREADS = 128, SA_KT = 64, SA_CH = 16;
-
-__global__ void __launch_bounds__(SA_THREADS)
-sig_attention_kernel(const float* __restrict__ qkv, ActImg out, const int* __restrict__ cu, int lpi) {
-  __shared__ __align__(16) float Ks[SA_KT][64];
-  __shared__ __align__(16) float Vs[SA_KT][64];
-  int lb, le;
-  image_range(cu, lpi, blockIdx.z, lb, le);
-  const int L = le - lb;
-  const int q0 = blockIdx.x * SA_THREADS;
-  if (q0 >= L) return;
-  const int h = blockIdx.y, tid = threadIdx.x;
-  const int qi = q0 + tid;
-  const bool active = qi < L;
-  float q[64], o[64];
-  {
-    const float* qp = qkv + (long long)(lb + (active ? qi : 0)) * 768 + h * 64;
-#pragma unroll
-    for (int d = 0; d < 64; d += 4) {
-      float4 t = *reinterpret_cast<const float4*>(qp + d);
-      q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < 64; ++d) o[d] = 0.f;
-  float m = -INFINITY, l = 0.f;
-
-  for (int k0 = 0; k0 < L; k0 += SA_KT) {
-    __syncthreads();
-    // stage K and V tiles: 64 keys x 16 float4 each, coalesced
-    for (int i = tid; i < SA_KT * 16; i += SA_THREADS) {
-      int j = i >> 4, c4 = (i & 15) * 4;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (k0 + j < L) {
-        const float* base = qkv + (long long)(lb + k0 + j) * 768 + h * 64 + c4;
-        kv = *reinterpret_cast<const float4*>(base + 256);
-        vv = *reinterpret_cast<const float4*>(base + 512);
-      }
-      *reinterpret_cast<float4*>(&Ks[j][c4]) = kv;
-      *reinterpret_cast<float4*>(&Vs[j][c4]) = vv;
-    }
-    __syncthreads();
-    const int kn = min(SA_KT, L - k0);
-    for (int c0 = 0; c0 < kn; c0 += SA_CH) {
-      float s[SA_CH];
-      float cmax = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < SA_CH; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < 64; d += 4) {
-          float4 kk = *reinterpret_cast<const float4*>(&Ks[c0 + j][d]);
-          a = fmaf(q[d], kk.x, a); a = fmaf(q[d + 1], kk.y, a);
-          a = fmaf(q[d + 2], kk.z, a); a = fmaf(q[d + 3], kk.w, a);
-        }
-        s[j] = (c0 + j < kn) ? a : -INFINITY;
-        cmax = fmaxf(cmax, s[j]);
-      }
-      float mn = fmaxf(m, cmax);
-      float scale = expf(m - mn);  // exp(-inf) = 0 on the first chunk
-      l *= scale;
-#pragma unroll
-      for (int d = 0; d < 64; ++d) o[d] *= scale;
-#pragma unroll
-      for (int j = 0; j < SA_CH; ++j) {
-        float pj = expf(s[j] - mn);
-        l += pj;
-#pragma unroll
-        for (int d = 0; d < 64; d += 4) {
-          float4 vv = *reinterpret_cast<const float4*>(&Vs[c0 + j][d]);
-          o[d] = fmaf(pj, vv.x, o[d]); o[d + 1] = fmaf(pj, vv.y, o[d + 1]);
-          o[d + 2] = fmaf(pj, vv.z, o[d + 2]); o[d + 3] = fmaf(pj, vv.w, o[d + 3]);
-        }
-      }
-      m = mn;
-    }
-  }
-  if (active) {
-    float inv = 1.f / l;
-#pragma unroll
-    for (int d = 0; d < 64; d += 8) {
-      const float v[8] = {o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv,
-                          o[d + 4] * inv, o[d + 5] * inv, o[d + 6] * inv, o[d + 7] * inv};
-      img_store8(out, lb + qi, h * 64 + d, v);
-    }
   }
 }
 

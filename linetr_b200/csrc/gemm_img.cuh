@@ -7,7 +7,7 @@
 // x ~= hi + lo), each a sequence of 16 KB tiles [m_tile = row/128][k_block = k/64] holding
 // 128 rows x 64 k in the K-major SWIZZLE_128B layout tcgen05 reads.  A tile is therefore ONE
 // contiguous cp.async.bulk (TMA) transfer and needs no CUDA-core work on the consumer side.
-// Weights use the same trick (TcWeight, linear_tc.cuh).
+// Weights use the same trick (TcWeight, tc_weight.cuh).
 //
 // The main loop is pure TMA + tcgen05:  warp 0 streams A and W tiles through an mbarrier
 // ring, warp 1 issues 3 MMAs per k-step (lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM),
@@ -18,7 +18,7 @@
 #pragma once
 #include "common.cuh"
 #include "linear_f32.cuh"
-#include "linear_tc.cuh"
+#include "tc_weight.cuh"
 #include "act_img.cuh"
 #include "ptx_sm100.cuh"
 
@@ -168,23 +168,6 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
       ptx::tc_fence_after();
       if (tl < 4 && warp == 2 && lane == 0) LTR_STAMP(tl * 16 + 3);
       const int row0 = mt * 128 + q * 32;   // first row of this warp
-#ifdef LTR_EPI_LD64_EXPERIMENT
-      if (!p.C && !p.O.hi) {   // timing experiment: drain the accumulator with 64-column loads only
-        float sink = 0.f;
-        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 64) {
-          float a64[64];
-          ptx::tmem_ld64(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c0, a64);
-#pragma unroll
-          for (int j = 0; j < 64; ++j) sink += a64[j];
-        }
-        if (sink == 123.456f && p.trace) p.trace[63] = 1;
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (tl < 4 && warp == 2 && lane == 0) LTR_STAMP(tl * 16 + 5);
-        if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
-        continue;
-      }
-#endif
 #pragma unroll 1
       for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         float acc[32];

@@ -1,6 +1,6 @@
 // fp32 CUDA-core GEMM engine: Y = act(X W^T + b) (+ R), row-major, W is [N, K].
 // Used for the narrow layers that stay on CUDA cores and as the numerics yardstick of the
-// tensor-core engine (linear_tc.cuh).  Replaces the aten addmm / MKLDNN conv1d(k=1)
+// tensor-core engine (tc_weight.cuh).  Replaces the aten addmm / MKLDNN conv1d(k=1)
 // calls of the reference (models/line_transformer.py:9-20, models/line_attention.py:55-57,
 // 69,89).
 #pragma once

@@ -10,7 +10,7 @@
 #include "common.cuh"
 #include "encoder_kernels.cuh"
 #include "linear_f32.cuh"
-#include "linear_tc.cuh"
+#include "tc_weight.cuh"
 #include "gemm_img.cuh"
 #include "token_fused.cuh"
 #include "sig_attention_tc.cuh"
@@ -79,7 +79,6 @@ struct LtrModel {
   ltr::Lin wv, wfc, w1, w2, wf;  // wv: 4 heads of [64,256]; wfc bias includes the CLS residual
   float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
   std::vector<ltr::SigLayer> sig;
-  int token_chunk = 32768;  // tokens per pass of the token stage (keeps intermediates in L2)
 };
 
 namespace ltr {
@@ -198,9 +197,8 @@ struct EncodeWs {
   ActImg z, ctx, y1i, g, l128, l256;  // images [R, 1024 / 256 / 256 / 1024 / 128 / 256]
   float *y1pre, *y1, *y2pre, *lpos;   // fp32 [R, 256]
   // signature stage
-  ActImg xm, o, hm;    // images [R, 512] = [x | message], [R, 256], [R, 512]
+  ActImg xm, hm;       // images [R, 512] = [x | attention output], [R, 512]
   float *xf, *qkv, *yf;  // fp32 [R, 256] running descriptor, [R, 768], [R, 256]
-  int chunk_lines;
   int64_t bytes;
 };
 
@@ -222,7 +220,6 @@ static EncodeWs carve(const LtrModel* m, int n_lines, int T, char* base) {
     return a;
   };
   (void)m; (void)T;
-  w.chunk_lines = 0;
   const int64_t R = n_lines;
   w.z = takei(R, 1024);
   w.ctx = takei(R, 256);
@@ -235,7 +232,6 @@ static EncodeWs carve(const LtrModel* m, int n_lines, int T, char* base) {
   w.y2pre = takef(R * 256);
   w.lpos = takef(R * 256);
   w.xm = takei(R, 512);
-  w.o = takei(R, 256);
   w.hm = takei(R, 512);
   w.xf = takef(R * 256);
   w.qkv = takef(R * 768);
@@ -563,10 +559,6 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   for (auto& o : so)
     m->sig.push_back({bind_lin(o.qkv, B, TB), bind_lin(o.merge, B, TB), bind_lin(o.mlp1, B, TB), bind_lin(o.mlp2, B, TB)});
   m->wf = bind_lin(oWf, B, TB);
-  if (const char* e = std::getenv("LINETR_TOKEN_CHUNK")) {
-    int v = std::atoi(e);
-    if (v > 0) m->token_chunk = v;
-  }
   *out = m;
   return LTR_OK;
 }
@@ -685,34 +677,6 @@ int ltr_linear(const float* x, int32_t ldx, const float* w, const float* bias, c
   if (!x || !w || !y) return set_error(LTR_E_INVALID, "ltr_linear: null argument");
   LTR_CUDA_TRY(cudaSetDevice(device));
   return launch_linear_f32(lin(x, ldx, w, bias, y, ldy, m, n, k, act, res, ldr), as_stream(stream));
-}
-
-int ltr_linear_tc(const float* x, int32_t ldx, const float* w_host, const float* bias, const float* res, int32_t ldr,
-                  float* y, int32_t ldy, int32_t m, int32_t n, int32_t k, int32_t act, int32_t device, void* stream) {
-  if (!x || !w_host || !y) return set_error(LTR_E_INVALID, "ltr_linear_tc: null argument");
-  if (n % 64 || k % 64) return set_error(LTR_E_UNSUPPORTED, "ltr_linear_tc: n and k must be multiples of 64");
-  LTR_CUDA_TRY(cudaSetDevice(device));
-  std::vector<double> W((size_t)n * k);
-  for (size_t i = 0; i < W.size(); ++i) W[i] = w_host[i];
-  std::vector<uint16_t> img(2 * (size_t)n * k);
-  pack_tc_weight(W.data(), n, k, img.data(), img.data() + (size_t)n * k);
-  uint16_t* d = nullptr;
-  LTR_CUDA_TRY(cudaMalloc(&d, img.size() * sizeof(uint16_t)));
-  cudaError_t ce = cudaMemcpy(d, img.data(), img.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
-  int rc = 0;
-  if (ce == cudaSuccess) {
-    TcArgs a{};
-    a.A = x; a.lda = ldx; a.bias = bias; a.R = res; a.ldr = ldr; a.C = y; a.ldc = ldy; a.M = m; a.act = act;
-    a.W.hi = reinterpret_cast<const __nv_bfloat16*>(d);
-    a.W.lo = reinterpret_cast<const __nv_bfloat16*>(d + (size_t)n * k);
-    a.W.N = n; a.W.K = k;
-    rc = launch_linear_tc(a, 1, as_stream(stream));
-    ce = cudaStreamSynchronize(as_stream(stream));
-  }
-  cudaFree(d);
-  if (rc != 0) return rc;
-  if (ce != cudaSuccess) return set_error(LTR_E_CUDA, std::string("ltr_linear_tc: ") + cudaGetErrorString(ce));
-  return LTR_OK;
 }
 
 int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float* bias, const float* res, int32_t ldr,

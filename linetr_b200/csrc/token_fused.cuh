@@ -10,8 +10,8 @@
 //       z_h = sum_n p_h[n] x[n]                                               -> z image (global)
 // Replaces WordPositionalEncoder (models/line_transformer.py:61-73), `desc + pos` and the CLS
 // concat (:117-121) and the attention part of MultiHeadAttention restricted to the CLS query row
-// (models/line_attention.py:13-21,55-63), i.e. what small_mlp_kernel<true> + 2 GEMM launches +
-// cls_pool_kernel did through global memory.  Only `desc` (the mandatory HBM read), the
+// (models/line_attention.py:13-21,55-63), i.e. what a narrow-MLP kernel, two GEMM launches and a
+// pooling kernel would do through global memory.  Only `desc` (the mandatory HBM read), the
 // weights (L2 resident, streamed by TMA through a 2-slot ring) and the pooled z leave/enter the SM.
 //
 // Warp roles: warp 0 = TMA weight producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-9 =
@@ -20,7 +20,7 @@
 #pragma once
 #include "act_img.cuh"
 #include "common.cuh"
-#include "linear_tc.cuh"
+#include "tc_weight.cuh"
 #include "ptx_sm100.cuh"
 
 namespace ltr {
@@ -33,7 +33,7 @@ struct TokenFusedArgs {
   const float *w1, *b1, *w2, *b2;
   TcWeight W3, W4, W5;  // [128,64], [256,128], [256,256] packed split-bf16
   const float *b3, *b4, *b5;
-  const float* U;      // [4,256] folded CLS query (see cls_pool_kernel)
+  const float* U;      // [4,256] folded CLS query u_h = W_k,h^T q_h / 8 (ltr_create)
   const float* s_cls;  // [4]
   const float* cls;    // [256]
   ActImg z;            // out: image of [R, 1024]
@@ -261,7 +261,6 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       const int line0 = tile * p.lpt;
       const long long tok0 = (long long)line0 * p.T;
       const long long n_tok_total = (long long)p.R * p.T;
-      const bool row_live = r_in < rows_used && tok0 + r_in < n_tok_total;
       const bool tr = (tile == blockIdx.x + gridDim.x) && warp == 2 && lane == 0;   // trace the CTA's 2nd tile
       if (tr) LTR_DBG_STAMP(0);
       // ---- P0 result of THIS tile (computed during the previous tile's L5 MMAs) -> h64 operand tile

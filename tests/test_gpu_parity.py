@@ -61,24 +61,6 @@ def test_linear_engine_vs_torch_fp32(M, N_, K, act):
     assert (got - want).abs().max().item() < 2e-5
 
 
-@pytest.mark.parametrize("M,N_,K,act", [(1, 64, 64, 0), (128, 64, 64, 0), (127, 256, 128, 1), (300, 768, 256, 0),
-                                        (513, 1024, 256, 2), (64, 256, 1024, 0), (2816, 256, 256, 0),
-                                        (130, 512, 512, 1), (200, 128, 256, 0)])
-def test_linear_tensor_core_engine_vs_fp64(M, N_, K, act):
-    """tcgen05 engine with split-bf16 operands (hi*hi + lo*hi + hi*lo) against an fp64 reference:
-    ~1e-5 relative, far inside the 1e-3 descriptor budget (plain bf16 would be ~1e-2)."""
-    g = torch.Generator().manual_seed(M * 7 + K + N_)
-    x = torch.randn(M, K, generator=g)
-    w = torch.randn(N_, K, generator=g) / K ** 0.5
-    b = torch.randn(N_, generator=g)
-    r = torch.randn(M, N_, generator=g)
-    want = torch.nn.functional.linear(x.double(), w.double(), b.double())
-    want = [want, torch.relu(want), torch.nn.functional.gelu(want)][act] + r.double()
-    got = _ops.linear(x.to(DEV), w, b.to(DEV), r.to(DEV), act, engine="tc").cpu().double()
-    err = (got - want).abs().max().item()
-    assert err < 1e-4, err
-
-
 @pytest.mark.parametrize("M,N_,K,act,bn", [(1, 128, 64, 0, 0), (128, 128, 64, 0, 128), (127, 256, 128, 1, 256),
                                            (300, 768, 256, 0, 256), (513, 1024, 256, 2, 0), (64, 256, 1024, 0, 128),
                                            (40000, 256, 256, 0, 256), (20000, 512, 512, 1, 0), (1000, 256, 512, 0, 128)])
@@ -155,19 +137,6 @@ def test_varlen_batch_equals_per_image():
         s, e = batch.cu_lines[i], batch.cu_lines[i + 1]
         assert np.abs(rows[s:e].T - want).max() < DESC_TOL_TIGHT
         assert np.abs(cf[256 * s:256 * e].reshape(256, e - s) - want).max() < DESC_TOL_TIGHT
-
-
-def test_token_chunking_is_invisible(monkeypatch):
-    """The token stage is processed in L2-sized chunks of lines; chunk size must not matter."""
-    sd = syn.make_state_dict(0, 1)
-    data = syn.make_image_inputs(5, 50, 21)
-    outs = []
-    for chunk in ("64", "1000000"):
-        monkeypatch.setenv("LINETR_TOKEN_CHUNK", chunk)
-        m = LineTransformer({"mode": "train"})
-        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
-        outs.append(fwd(m.eval().to(DEV), data))
-    assert np.array_equal(outs[0], outs[1])
 
 
 def test_weight_update_repacks():
