@@ -29,6 +29,7 @@ struct GemmImgArgs {
   TcWeight W;
   const float* bias;
   const float* R; int ldr;   // fp32 residual (added after the activation) or nullptr
+  ActImg Rimg; int r_kb0;    // OR: residual read from a split-bf16 image (hi + lo), k-block offset
   float* C; int ldc;         // fp32 output or nullptr
   ActImg O; int o_kb0;       // image output (O.hi == nullptr: none); column n -> k-block o_kb0 + n/64
   int M, act;
@@ -204,6 +205,40 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 v = *reinterpret_cast<const float4*>(&stg[lane * 32 + ((c4 ^ (lane & 7)) << 2)]);
             acc[c4 * 4] += v.x; acc[c4 * 4 + 1] += v.y; acc[c4 * 4 + 2] += v.z; acc[c4 * 4 + 3] += v.w;
+          }
+          __syncwarp();
+        }
+        if (p.Rimg.hi) {
+          // residual from a split-bf16 image: coalesced 16-byte chunk loads -> staging -> own row
+          const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
+          const uint8_t* rhi = reinterpret_cast<const uint8_t*>(p.Rimg.hi + rtoff);
+          const uint8_t* rlo = reinterpret_cast<const uint8_t*>(p.Rimg.lo + rtoff);
+          const int gch0r = (nbase & 63) >> 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = i * 8 + (lane >> 2), cc = lane & 3;
+            uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+            if (row0 + rl < p.M) {
+              const uint32_t off = ptx::sw128_offset(q * 32 + rl, (gch0r + cc) * 8);
+              vh = *reinterpret_cast<const uint4*>(rhi + off);
+              vl = *reinterpret_cast<const uint4*>(rlo + off);
+            }
+            const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
+            *reinterpret_cast<uint4*>(stgb + slot) = vh;
+            *reinterpret_cast<uint4*>(stgb + 2048 + slot) = vl;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int slot = (lane * 4 + (cc ^ ((lane >> 1) & 3))) * 16;
+            const uint4 vh = *reinterpret_cast<const uint4*>(stgb + slot);
+            const uint4 vl = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
+            const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {   // bf16 -> fp32 is a 16-bit shift
+              acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
+              acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
+            }
           }
           __syncwarp();
         }

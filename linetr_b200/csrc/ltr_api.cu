@@ -198,7 +198,7 @@ struct EncodeWs {
   float *y1pre, *y1, *y2pre, *lpos;   // fp32 [R, 256]
   // signature stage
   ActImg xm, hm;       // images [R, 512] = [x | attention output], [R, 512]
-  float *xf, *qkv, *yf;  // fp32 [R, 256] running descriptor, [R, 768], [R, 256]
+  float *qkv, *yf;       // fp32 [R, 768] (attention gather), [R, 256] (final projection)
   int64_t bytes;
 };
 
@@ -233,7 +233,6 @@ static EncodeWs carve(const LtrModel* m, int n_lines, int T, char* base) {
   w.lpos = takef(R * 256);
   w.xm = takei(R, 512);
   w.hm = takei(R, 512);
-  w.xf = takef(R * 256);
   w.qkv = takef(R * 768);
   w.yf = takef(R * 256);
   w.bytes = off;
@@ -251,10 +250,12 @@ static LinearArgs lin(const float* A, int lda, const float* W, const float* b, f
 // One wide layer on the tensor-core engine: A image k-blocks [a_kb0, a_kb0 + K/64) -> fp32 rows C
 // (optional) and/or image O k-blocks from o_kb0 (optional); R = fp32 residual.
 static int gemm(const Lin& L, const ActImg& A, int a_kb0, int M, int act, cudaStream_t s, float* C, int ldc,
-                const ActImg* O = nullptr, int o_kb0 = 0, const float* R = nullptr, int ldr = 0) {
+                const ActImg* O = nullptr, int o_kb0 = 0, const float* R = nullptr, int ldr = 0,
+                const ActImg* Rimg = nullptr, int r_kb0 = 0) {
   GemmImgArgs a{};
   a.A = A; a.a_kb0 = a_kb0; a.W = L.tw; a.bias = L.b; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc;
   if (O) { a.O = *O; a.o_kb0 = o_kb0; }
+  if (Rimg) { a.Rimg = *Rimg; a.r_kb0 = r_kb0; }
   a.M = M; a.act = act;
   return launch_gemm_img(a, s);
 }
@@ -322,8 +323,8 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
                                   in.image_height, s));
   LTR_TRY(gemm(m->lpe.l4, w.l128, 0, R, ACT_RELU, s, nullptr, 0, &w.l256, 0));
   LTR_TRY(gemm(m->lpe.l5, w.l256, 0, R, ACT_NONE, s, w.lpos, 256));
-  // sentence = klines_pos + LN(ffn)  -> fp32 running descriptor xf and image xm[:, :256]
-  LTR_TRY(launch_layernorm(w.y2pre, 256, m->ln2g, m->ln2b, w.lpos, 256, w.xf, 256, w.xm, 0, R, s));
+  // sentence = klines_pos + LN(ffn)  -> image xm[:, :256] (the running descriptor)
+  LTR_TRY(launch_layernorm(w.y2pre, 256, m->ln2g, m->ln2b, w.lpos, 256, nullptr, 0, w.xm, 0, R, s));
   // ---- line signature layers ----
   int max_l = in.lines_per_image;
   if (in.cu_lines_host) {
@@ -335,7 +336,9 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
     LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, w.qkv, 768));
     LTR_TRY(launch_sig_attention_tc(w.qkv, w.xm, 256, cu, in.lines_per_image, max_l, in.n_images, s));  // o -> xm[:, 256:]
     LTR_TRY(gemm(L.mlp1, w.xm, 0, R, ACT_RELU, s, nullptr, 0, &w.hm, 0));
-    LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, w.xf, 256, &w.xm, 0, w.xf, 256));  // x += delta
+    // x += delta: the running descriptor lives ONLY as the split-bf16 image xm[:, :256] (hi + lo carries
+    // ~2^-17 relative precision; an fp32 copy would double the store traffic of this epilogue)
+    LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, nullptr, 0, &w.xm, 0, nullptr, 0, &w.xm, 0));
   }
   LTR_TRY(gemm(m->wf, w.xm, 0, R, ACT_NONE, s, w.yf, 256));
   if (max_l > 0) {
