@@ -113,7 +113,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def result(self):
         self.stop_flag = True
