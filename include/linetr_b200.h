@@ -169,6 +169,36 @@ int ltr_merge_sublines(const float* dist_sub, int64_t stride_sub, int32_t n_pair
                        const int32_t* sub_off1, int32_t max_k0, int32_t max_k1, float* dist_key,
                        int64_t stride_key, int32_t device, void* stream);
 
+/* GPU line tokenizer - the step that feeds ltr_encode (reference line_tokenizer +
+ * sample_descriptors, models/line_process.py:86-196).  The host supplies per key line (device
+ * arrays): start point, end point before and after the in-place clip to (W-0.6, H-0.6) [K,2]
+ * float64, detector length [K] float64, angle code [K,2] float32, n_tok = ceil(length /
+ * token_distance) [K], first subline index sub0 [K+1] and the key line of every subline [S].
+ * Outputs (device, fp32) in the tokenizer's layout: sublines [S,2,2], pnt [S,T,2], mask
+ * [S,T+1,1], resp [S,1], angle [S,2], desc [S,T,256] (bilinear grid_sample of dense_desc
+ * [256,desc_h,desc_w] + L2 normalisation), score [S,T,1] (dense_score [score_h,score_w] at the
+ * rounded token position). */
+typedef struct {
+  const double* sp;
+  const double* ep;
+  const double* ep_clipped;
+  const double* length;
+  const float* angle;
+  const int32_t* n_tok;
+  const int32_t* sub0;
+  const int32_t* sub2line;
+  int32_t n_keylines, n_sublines, n_tokens;
+  double token_distance;
+  const float* dense_desc;
+  int32_t desc_channels, desc_h, desc_w;
+  const float* dense_score;
+  int32_t score_h, score_w;
+  int32_t align_corners;   /* the reference keys this on the torch version (line_process.py:93) */
+} LtrTokenizeInput;
+
+int ltr_tokenize(const LtrTokenizeInput* in, float* sublines, float* pnt, float* mask, float* resp,
+                 float* angle, float* desc, float* score, int32_t device, void* stream);
+
 /* Generic row-major linear layer Y = act(X W^T + b) (+ R) on the library's GEMM engine;
  * exported so the engine can be unit-tested in isolation.  act: 0 none, 1 relu, 2 gelu(erf). */
 int ltr_linear(const float* x, int32_t ldx, const float* w, const float* bias, const float* res,

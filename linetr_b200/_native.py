@@ -21,7 +21,7 @@ LAYOUT_CHANNEL_FIRST = 1
 # Every symbol include/linetr_b200.h declares (tests check the library exports all of them).
 EXPORTED_SYMBOLS = (
     "ltr_abi_version", "ltr_last_error", "ltr_create", "ltr_destroy", "ltr_encode_workspace_bytes",
-    "ltr_encode", "ltr_match", "ltr_match_distmat", "ltr_merge_sublines", "ltr_linear", "ltr_linear_img", "ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read", "ltr_launch_count",
+    "ltr_encode", "ltr_match", "ltr_match_distmat", "ltr_merge_sublines", "ltr_tokenize", "ltr_linear", "ltr_linear_img", "ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read", "ltr_launch_count",
     "ltr_reset_launch_count", "ltr_profile_begin", "ltr_profile_end",
 )
 
@@ -61,6 +61,15 @@ class LtrMatchOutput(C.Structure):
                 ("counts", C.c_void_p), ("dist_key", C.c_void_p), ("dist_sub", C.c_void_p)]
 
 
+class LtrTokenizeInput(C.Structure):
+    _fields_ = [("sp", C.c_void_p), ("ep", C.c_void_p), ("ep_clipped", C.c_void_p), ("length", C.c_void_p),
+                ("angle", C.c_void_p), ("n_tok", C.c_void_p), ("sub0", C.c_void_p), ("sub2line", C.c_void_p),
+                ("n_keylines", C.c_int32), ("n_sublines", C.c_int32), ("n_tokens", C.c_int32),
+                ("token_distance", C.c_double), ("dense_desc", C.c_void_p), ("desc_channels", C.c_int32),
+                ("desc_h", C.c_int32), ("desc_w", C.c_int32), ("dense_score", C.c_void_p), ("score_h", C.c_int32),
+                ("score_w", C.c_int32), ("align_corners", C.c_int32)]
+
+
 def lib_path() -> str:
     return _LIB_PATH
 
@@ -97,6 +106,8 @@ def load():
                                        C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                        C.c_void_p]
     lib.ltr_merge_sublines.restype = C.c_int
+    lib.ltr_tokenize.argtypes = [C.POINTER(LtrTokenizeInput)] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p]
+    lib.ltr_tokenize.restype = C.c_int
     lib.ltr_linear.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.ltr_linear.restype = C.c_int

@@ -35,6 +35,7 @@ enum KernelClass : int {
   KC_TOKEN_FUSED,
   KC_LINE_FUSED,
   KC_SIG_FUSED,
+  KC_TOKENIZE,
   KC_COUNT
 };
 const char* kernel_class_name(int kc);

@@ -14,6 +14,7 @@
 #include "gemm_img.cuh"
 #include "token_fused.cuh"
 #include "sig_attention_tc.cuh"
+#include "tokenizer_kernels.cuh"
 #include "match_kernels.cuh"
 
 namespace ltr {
@@ -30,7 +31,7 @@ int set_error(int code, const std::string& msg) {
 const char* kernel_class_name(int kc) {
   static const char* names[KC_COUNT] = {"small_mlp", "linear", "cls_pool", "layernorm", "sig_attention",
                                          "final_norm", "dist", "segmean", "argmin", "mutual",
-                                         "token_fused", "line_fused", "sig_fused"};
+                                         "token_fused", "line_fused", "sig_fused", "tokenize"};
   return (kc >= 0 && kc < KC_COUNT) ? names[kc] : "?";
 }
 
@@ -672,6 +673,35 @@ int ltr_merge_sublines(const float* dist_sub, int64_t stride_sub, int32_t n_pair
   LaunchScope ls(KC_SEGMEAN, s);
   segmean_kernel<<<dim3(cdiv(max_k1, 32), cdiv(max_k0, 8), n_pairs), 256, 0, s>>>(sa);
   LTR_CUDA_TRY(cudaGetLastError());
+  return LTR_OK;
+}
+
+int ltr_tokenize(const LtrTokenizeInput* in, float* sublines, float* pnt, float* mask, float* resp, float* angle,
+                 float* desc, float* score, int32_t device, void* stream) {
+  if (!in || !sublines || !pnt || !mask || !resp || !angle || !desc || !score)
+    return set_error(LTR_E_INVALID, "ltr_tokenize: null argument");
+  if (in->n_sublines <= 0 || in->n_keylines <= 0) return LTR_OK;
+  if (in->n_tokens < 1 || in->desc_channels != 256)
+    return set_error(LTR_E_UNSUPPORTED, "ltr_tokenize: n_tokens >= 1 and 256 descriptor channels required");
+  if (!in->sp || !in->ep || !in->ep_clipped || !in->length || !in->angle || !in->n_tok || !in->sub0 || !in->sub2line ||
+      !in->dense_desc || !in->dense_score)
+    return set_error(LTR_E_INVALID, "ltr_tokenize: null input array");
+  LTR_CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = as_stream(stream);
+  TokLines L{in->sp, in->ep, in->ep_clipped, in->length, in->angle, in->n_tok, in->sub0, in->sub2line,
+             in->n_keylines, in->n_sublines, in->n_tokens, in->token_distance};
+  const long long n_tok = (long long)in->n_sublines * in->n_tokens;
+  {
+    LaunchScope ls(KC_TOKENIZE, s);
+    tok_points_kernel<<<cdiv(n_tok, 256), 256, 0, s>>>(L, pnt, mask, sublines, resp, angle);
+    LTR_CUDA_TRY(cudaGetLastError());
+  }
+  {
+    LaunchScope ls(KC_TOKENIZE, s);
+    tok_sample_kernel<<<cdiv(n_tok, 8), 256, 0, s>>>(pnt, (int)n_tok, in->dense_desc, in->desc_h, in->desc_w, in->dense_score,
+                                                      in->score_h, in->score_w, in->align_corners, desc, score);
+    LTR_CUDA_TRY(cudaGetLastError());
+  }
   return LTR_OK;
 }
 

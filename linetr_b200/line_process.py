@@ -1,11 +1,14 @@
-"""Host-side glue around the hot path: `get_dist_matrix` (CUDA) and the line tokeniser (CPU).
+"""`get_dist_matrix` (CUDA) and the line tokeniser that feeds the hot path.
 
 `get_dist_matrix` is on the hot path (reference models/line_process.py:198-201) and runs on
-the GPU through `ltr_match`.  Everything else here is the tokeniser that *feeds* the hot path
-(reference models/line_process.py:6-196; SURVEY.md §8f row 1, "next"): it stays numpy/PyTorch
-glue in this round and is written to reproduce the reference's outputs exactly - including
-its quirks (in-place end-point clipping, `index[:max_keylines]` dropping the shortest line when
-max_keylines == -1, the torch-version dependent `align_corners`).
+the GPU through `ltr_match`.  The tokeniser (reference models/line_process.py:6-196; SURVEY.md
+§8f row 1, the first "next" row) exists twice: `line_tokenizer_gpu` (CUDA, `ltr_tokenize`; used by
+`LineTransformer.preprocess` whenever the SuperPoint outputs live on a CUDA device) and
+`line_tokenizer`, numpy/PyTorch glue that reproduces the reference bit for bit - including its
+quirks (in-place end-point clipping, `index[:max_keylines]` dropping the shortest line when
+max_keylines == -1, the torch-version dependent `align_corners`) - and is the pin the GPU
+tokeniser is tested against.  The cheap per-image filters (`remove_borders`,
+`filter_by_length`, cv2 KeyLine conversion) stay vectorised numpy.
 """
 from __future__ import annotations
 
@@ -175,4 +178,73 @@ def line_tokenizer(klines, token_distance, max_tokens, pred_superpoint, image_sh
     klines["desc_sublines"] = desc[None]
     klines["score_sublines"] = scores[None]
     klines["mat_klines2sublines"] = adj[None]
+    return klines
+
+
+def line_tokenizer_gpu(klines, token_distance, max_tokens, pred_superpoint, image_shape):
+    """`line_tokenizer` on the GPU (ltr_tokenize): same inputs, same output dict, no Python loops.
+    Token positions, sublines, masks, responses and the adjacency are bit-identical to the CPU
+    version (float64 arithmetic, rounded once to fp32); sampled descriptors agree to fp32 rounding."""
+    import ctypes as C
+    from . import _native as N
+    dense = pred_superpoint["dense_descriptor"]
+    if not dense.is_cuda:
+        raise N.LtrError("line_tokenizer_gpu needs the SuperPoint outputs on a CUDA device")
+    dev = dense.device
+    height, width = image_shape
+    T = int(max_tokens)
+    kl = klines["klines"]
+    K = len(kl)
+    length = np.ascontiguousarray(klines["length_klines"], dtype=np.float64)
+    n_tok = np.ceil(length / token_distance).astype(np.int64)
+    n_sub = -(-n_tok // T)
+    geo = np.sqrt(((kl[:, 1] - kl[:, 0]) ** 2).sum(axis=1))
+    assert bool((geo >= np.maximum(n_tok - 2, 0) * token_distance).all()), "distance should be smaller than line length!"
+    sp = np.ascontiguousarray(kl[:, 0], dtype=np.float64)
+    ep = np.ascontiguousarray(kl[:, 1], dtype=np.float64).copy()
+    kl[:, 1, 0] = np.minimum(kl[:, 1, 0], width - 0.6)      # in place, like the reference
+    kl[:, 1, 1] = np.minimum(kl[:, 1, 1], height - 0.6)
+    epc = np.ascontiguousarray(kl[:, 1], dtype=np.float64)
+    sub0 = np.zeros(K + 1, dtype=np.int64)
+    sub0[1:] = np.cumsum(n_sub)
+    S = int(sub0[-1])
+    sub2line = np.repeat(np.arange(K), n_sub)
+    angles = np.ascontiguousarray(klines["angles"], dtype=np.float32)
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    d_sp, d_ep, d_epc, d_len = up(sp, np.float64), up(ep, np.float64), up(epc, np.float64), up(length, np.float64)
+    d_ang, d_ntok, d_sub0, d_s2l = up(angles, np.float32), up(n_tok, np.int32), up(sub0, np.int32), up(sub2line, np.int32)
+    f32 = dict(dtype=torch.float32, device=dev)
+    slines = torch.empty((S, 2, 2), **f32)
+    tokens = torch.empty((S, T, 2), **f32)
+    masks = torch.empty((S, T + 1, 1), **f32)
+    responses = torch.empty((S, 1), **f32)
+    ang = torch.empty((S, 2), **f32)
+    desc = torch.empty((S, T, 256), **f32)
+    scores = torch.empty((S, T, 1), **f32)
+    dense_c = dense.float().contiguous()
+    score_map = pred_superpoint["dense_score"].float().contiguous()
+    b, c, hc, wc = dense_c.shape
+    inp = N.LtrTokenizeInput(d_sp.data_ptr(), d_ep.data_ptr(), d_epc.data_ptr(), d_len.data_ptr(), d_ang.data_ptr(),
+                             d_ntok.data_ptr(), d_sub0.data_ptr(), d_s2l.data_ptr(), K, S, T, float(token_distance),
+                             dense_c.data_ptr(), c, hc, wc, score_map.data_ptr(), score_map.shape[-2], score_map.shape[-1],
+                             1 if int(torch.__version__[2]) > 2 else 0)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    with torch.cuda.device(dev):
+        rc = N.load().ltr_tokenize(C.byref(inp), p(slines), p(tokens), p(masks), p(responses), p(ang), p(desc), p(scores),
+                                   dev.index, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    N.check(rc, "ltr_tokenize")
+    adj = np.zeros((K, S), dtype=np.float32)
+    w = (1.0 / n_sub).astype(np.float64)
+    adj[sub2line, np.arange(S)] = w[sub2line]
+    klines["klines"] = torch.from_numpy(klines["klines"]).float().to(dev)[None]
+    klines["length_klines"] = torch.from_numpy(klines["length_klines"]).float().to(dev)[None]
+    klines["angles"] = torch.from_numpy(np.asarray(klines["angles"])).float().to(dev)[None]
+    klines["sublines"] = slines[None]
+    klines["pnt_sublines"] = tokens[None]
+    klines["mask_sublines"] = masks[None]
+    klines["resp_sublines"] = responses[None]
+    klines["angle_sublines"] = ang[None]
+    klines["desc_sublines"] = desc[None]
+    klines["score_sublines"] = scores[None]
+    klines["mat_klines2sublines"] = torch.from_numpy(adj).to(dev)[None]
     return klines

@@ -192,8 +192,8 @@ class LineTransformer(nn.Module):
         klines = LP.filter_by_length(klines, self.config["min_length"], self.config["max_keylines"])
         if len(klines["klines"]) == 0:
             return klines
-        return LP.line_tokenizer(klines, self.config["token_distance"], self.config["max_tokens"], pred_superpoint,
-                                 image_shape[-2:])
+        tok = LP.line_tokenizer_gpu if pred_superpoint["dense_descriptor"].is_cuda else LP.line_tokenizer
+        return tok(klines, self.config["token_distance"], self.config["max_tokens"], pred_superpoint, image_shape[-2:])
 
     def subline2keyline(self, distance_sublines, mat_klines2sublines0, mat_klines2sublines1):
         """A0 @ D @ A1^T on the GPU (reference models/line_transformer.py:277-282) -> np [1,K0,K1]."""

@@ -377,3 +377,26 @@ def test_cfg4_matcher_only_1024_exact():
     idx = orc.match_indices(mat)
     ok = idx >= 0
     assert ok.sum() >= 1000 and np.array_equal(perm[idx[ok]], np.nonzero(ok)[0])
+
+
+@pytest.mark.parametrize("cfg", [{}, {"max_tokens": 8, "token_distance": 12}, {"min_length": 40, "max_keylines": 20}])
+def test_gpu_tokenizer_equals_cpu_glue(cfg):
+    """ltr_tokenize (GPU) vs the CPU tokenizer glue, which tests/test_tokenizer.py pins bit-exactly to
+    the reference: geometry/masks/adjacency identical, sampled descriptors to fp32 rounding."""
+    from tests.test_tokenizer import fake_lines, fake_superpoint
+    sp = fake_superpoint(7)
+    sp_dev = {k: v.to(DEV) for k, v in sp.items()}
+    m = LineTransformer({"mode": "train", **cfg})
+    want = m.preprocess(fake_lines(7, 60), (1, 1, 480, 640), sp, None)
+    got = m.preprocess(fake_lines(7, 60), (1, 1, 480, 640), sp_dev, None)
+    assert set(want.keys()) == set(got.keys())
+    for k in want:
+        g = got[k].cpu()
+        assert g.shape == want[k].shape, k
+        if k == "desc_sublines":
+            assert (g - want[k]).abs().max().item() < 2e-6, k
+        else:
+            assert torch.equal(g, want[k]), k
+    # and the tokenised dict drives the encoder
+    out = m.eval().to(DEV)(got)["line_desc"]
+    assert out.shape[1] == 256 and torch.isfinite(out).all()
