@@ -70,6 +70,31 @@ struct LaunchScope {
   }
 };
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the path is launched with programmaticStreamSerialization: its CTAs may become
+// resident as soon as SMs free up at the tail of the previous kernel and run their prologue
+// (barrier init, TMEM allocation, constant staging) there; pdl_wait() then blocks until the
+// previous grid has completed and flushed, BEFORE anything it produced is read or anything it
+// still reads is overwritten.  pdl_launch_dependents() at kernel entry lets the next kernel do
+// the same behind this one.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- debug tracing (clock64 stamps of CTA 0)
 __device__ unsigned long long g_dbg_trace[128];
 __device__ int g_dbg_on = 0;

@@ -46,6 +46,7 @@ small_mlp_kernel(SmallMlpWeights w, const float* __restrict__ in0, const float* 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto& S = *reinterpret_cast<SmallMlpSmem<IN>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
   for (int i = tid; i < 32 * IN; i += blockDim.x) S.w1[i] = w.w1[i];
   for (int i = tid; i < 32; i += blockDim.x) S.b1[i] = w.b1[i];
   for (int i = tid; i < 64; i += blockDim.x) S.b2[i] = w.b2[i];
@@ -53,6 +54,7 @@ small_mlp_kernel(SmallMlpWeights w, const float* __restrict__ in0, const float* 
   for (int i = tid; i < 64 * 32; i += blockDim.x) S.w2[(i >> 5) * SM_K2 + (i & 31)] = w.w2[i];
   for (int i = tid; i < 128 * 64; i += blockDim.x) S.w3[(i >> 6) * SM_K3 + (i & 63)] = w.w3[i];
   __syncthreads();
+  pdl_wait();
 
   const int groups = (rows + SM_ROWS - 1) / SM_ROWS;
   for (int g = blockIdx.x * SM_WARPS + warp; g < groups; g += gridDim.x * SM_WARPS) {
@@ -162,6 +164,8 @@ layernorm256_kernel(const float* __restrict__ in, int ldi, const float* __restri
                     const float* __restrict__ beta, const float* __restrict__ add, int lda,
                     float* __restrict__ out, int ldo, ActImg oimg, int o_k0, int rows, float eps) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   const float* p = in + (long long)row * ldi;
   float4 a = *reinterpret_cast<const float4*>(p + lane * 4);
@@ -202,6 +206,8 @@ __global__ void __launch_bounds__(256)
 final_norm_kernel(const float* __restrict__ y, float* __restrict__ out_rows, float* __restrict__ out_cf,
                   const int* __restrict__ cu, int lpi) {
   __shared__ float tile[32][257];
+  pdl_launch_dependents();
+  pdl_wait();
   int lb, le;
   image_range(cu, lpi, blockIdx.y, lb, le);
   const int L = le - lb, l0 = blockIdx.x * 32;

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk = p.W.K / 64;
   const int n_tiles = p.m_tiles * p.n_blks;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // the previous kernel's outputs (A image, residual) are complete and visible from here on
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -326,8 +328,7 @@ static int launch_gemm_img_bn(GemmImgArgs a, cudaStream_t s) {
   const int tiles = a.m_tiles * a.n_blks;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   LaunchScope ls(KC_LINEAR, s);
-  gemm_img_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(a);
-  LTR_CUDA_TRY(cudaGetLastError());
+  LTR_CUDA_TRY(launch_pdl(gemm_img_kernel<BN>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, s, a));
   return 0;
 }
 

@@ -277,8 +277,8 @@ static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const fl
   if (grid > 148 * 3) grid = 148 * 3;
   const float scale = fmaxf(width, height) * 0.7f;
   LaunchScope ls(KC_SMALL_MLP, s);
-  small_mlp_kernel<TOKEN><<<grid, SM_WARPS * 32, smem, s>>>(w, in0, in1, in2, out, rows, width / 2.f, height / 2.f, scale);
-  LTR_CUDA_TRY(cudaGetLastError());
+  LTR_CUDA_TRY(launch_pdl(small_mlp_kernel<TOKEN>, dim3(grid), dim3(SM_WARPS * 32), (size_t)smem, s, w, in0, in1, in2, out, rows,
+                          width / 2.f, height / 2.f, scale));
   return 0;
 }
 
@@ -286,8 +286,8 @@ static int launch_layernorm(const float* in, int ldi, const float* g, const floa
                             float* out, int ldo, ActImg oimg, int o_k0, int rows, cudaStream_t s) {
   if (rows <= 0) return 0;
   LaunchScope ls(KC_LAYERNORM, s);
-  layernorm256_kernel<<<cdiv(rows, 8), 256, 0, s>>>(in, ldi, g, b, add, lda, out, ldo, oimg, o_k0, rows, 1e-6f);
-  LTR_CUDA_TRY(cudaGetLastError());
+  LTR_CUDA_TRY(launch_pdl(layernorm256_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, s, in, ldi, g, b, add, lda, out, ldo, oimg, o_k0,
+                          rows, 1e-6f));
   return 0;
 }
 
@@ -345,8 +345,7 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   if (max_l > 0) {
     LaunchScope ls(KC_FINAL_NORM, s);
     dim3 grid(cdiv(max_l, 32), in.n_images);
-    final_norm_kernel<<<grid, 256, 0, s>>>(w.yf, out_rows, out_cf, cu, in.lines_per_image);
-    LTR_CUDA_TRY(cudaGetLastError());
+    LTR_CUDA_TRY(launch_pdl(final_norm_kernel, grid, dim3(256), 0, s, (const float*)w.yf, out_rows, out_cf, cu, in.lines_per_image));
   }
   return 0;
 }

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
   const int qd = warp & 3, half = warp >> 2;
   const int row = qd * 32 + lane;   // query row of this thread (shared with its pair thread)
   if (tid == 0) LTR_DBG_STAMP(30);
+  pdl_launch_dependents();
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
   const uint32_t t_o = tmem_base + 128;    // O: 64 columns
   const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
   uint32_t phase = 0;
+  pdl_wait();   // qkv of this layer is complete; the previous reader of the output image is done
   if (tid == 0) LTR_DBG_STAMP(31);
 
   // Coalesced gather of a [128 rows x 64] fp32 tile (rows row0.. of the image, column offset col)
@@ -260,8 +262,7 @@ inline int launch_sig_attention_tc(const float* qkv, ActImg out, int out_k0, con
   }
   dim3 grid(cdiv(max_l, 128), 4, n_images);
   LaunchScope ls(KC_SIG_ATTN, s);
-  sig_attention_tc_kernel<<<grid, 256, SigAttnSmem::TOTAL, s>>>(qkv, out, out_k0, cu, lpi);
-  LTR_CUDA_TRY(cudaGetLastError());
+  LTR_CUDA_TRY(launch_pdl(sig_attention_tc_kernel, grid, dim3(256), SigAttnSmem::TOTAL, s, qkv, out, out_k0, cu, lpi));
   return 0;
 }
 

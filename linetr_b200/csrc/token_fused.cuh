@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
 
   for (int i = tid; i < 96; i += blockDim.x) sW1[i] = p.w1[i];
   for (int i = tid; i < 32; i += blockDim.x) sB1[i] = p.b1[i];
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // z (output image) may still be read by the previous launch sequence
 
   if (warp == 0) {
     // ---------------------------------------------------------------- W producer: 13 slots per tile
@@ -423,8 +425,7 @@ inline int launch_token_fused(TokenFusedArgs a, cudaStream_t s) {
   const int sms = 148;
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
   LaunchScope ls(KC_TOKEN_FUSED, s);
-  token_fused_kernel<<<grid, 320, TokenFusedSmem::TOTAL, s>>>(a);
-  LTR_CUDA_TRY(cudaGetLastError());
+  LTR_CUDA_TRY(launch_pdl(token_fused_kernel, dim3(grid), dim3(320), TokenFusedSmem::TOTAL, s, a));
   return 0;
 }
 
