@@ -351,22 +351,21 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
 }
 
 static int run_nn(const NNArgs& a, int n_pairs, int max_k0, int max_k1, cudaStream_t s) {
-  LTR_CUDA_TRY(cudaMemsetAsync(a.counts, 0, sizeof(int) * n_pairs, s));
-  if (max_k0 <= 0) return 0;
+  if (max_k0 <= 0) {
+    LTR_CUDA_TRY(cudaMemsetAsync(a.counts, 0, sizeof(int) * n_pairs, s));
+    return 0;
+  }
   {
-    LaunchScope ls(KC_ARGMIN, s);
-    row_argmin_kernel<<<dim3(cdiv(max_k0, 8), n_pairs), 256, 0, s>>>(a);
-    LTR_CUDA_TRY(cudaGetLastError());
+    LaunchScope ls(KC_ARGMIN, s);   // also zeroes counts[pair]
+    LTR_CUDA_TRY(launch_pdl(row_argmin_kernel, dim3(cdiv(max_k0, 8), n_pairs), dim3(256), 0, s, a));
   }
   if (a.mutual && max_k1 > 0) {
     LaunchScope ls(KC_ARGMIN, s);
-    col_argmin_kernel<<<dim3(cdiv(max_k1, 32), n_pairs), 256, 0, s>>>(a);
-    LTR_CUDA_TRY(cudaGetLastError());
+    LTR_CUDA_TRY(launch_pdl(col_argmin_kernel, dim3(cdiv(max_k1, 32), n_pairs), dim3(256), 0, s, a));
   }
   {
     LaunchScope ls(KC_MUTUAL, s);
-    mutual_kernel<<<dim3(cdiv(max_k0, 256), n_pairs), 256, 0, s>>>(a);
-    LTR_CUDA_TRY(cudaGetLastError());
+    LTR_CUDA_TRY(launch_pdl(mutual_kernel, dim3(cdiv(max_k0, 256), n_pairs), dim3(256), 0, s, a));
   }
   return 0;
 }
@@ -415,7 +414,7 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   if (!tensors || !cfg || !out) return set_error(LTR_E_INVALID, "ltr_create: null argument");
   if (cfg->d_model != 256 || cfg->n_heads != 4)
     return set_error(LTR_E_UNSUPPORTED, "ltr_create: kernels are specialised for d_model=256, n_heads=4");
-  if (cfg->d_inner <= 0 || cfg->d_inner % 64 || cfg->n_desc_layers < 1 || cfg->n_sig_layers < 0)
+  if (cfg->d_inner <= 0 || cfg->d_inner % 128 || cfg->n_desc_layers < 1 || cfg->n_sig_layers < 0)
     return set_error(LTR_E_INVALID, "ltr_create: bad d_inner / layer counts");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -627,9 +626,8 @@ int ltr_match(const LtrMatchInput* in, const LtrMatchOutput* out, int32_t device
     dim3 grid(cdiv(mx0, DK_BM), cdiv(mx1, DK_BN), in->n_pairs);
     {
       LaunchScope ls(KC_DIST, s);
-      if (in->layout == LTR_LAYOUT_CHANNEL_FIRST) dist_kernel<true><<<grid, DK_THREADS, 0, s>>>(da);
-      else dist_kernel<false><<<grid, DK_THREADS, 0, s>>>(da);
-      LTR_CUDA_TRY(cudaGetLastError());
+      if (in->layout == LTR_LAYOUT_CHANNEL_FIRST) LTR_CUDA_TRY(launch_pdl(dist_kernel<true>, grid, dim3(DK_THREADS), 0, s, da));
+      else LTR_CUDA_TRY(launch_pdl(dist_kernel<false>, grid, dim3(DK_THREADS), 0, s, da));
     }
     if (seg && mk0 > 0 && mk1 > 0) {
       SegMeanArgs sa{out->dist_sub, (long long)mx0 * mx1, out->dist_key, stride_key, in->cuk0, in->cuk1, in->sub_off0, in->sub_off1};

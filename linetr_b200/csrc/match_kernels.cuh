@@ -27,6 +27,8 @@ template <bool CF>
 __global__ void __launch_bounds__(DK_THREADS) dist_kernel(DistArgs p) {
   __shared__ __align__(16) float As[DK_BK][DK_BM + 4];
   __shared__ __align__(16) float Bs[DK_BK][DK_BN + 4];
+  pdl_launch_dependents();
+  pdl_wait();
   const int pair = blockIdx.z;
   int b0, e0, b1, e1;
   image_range(p.cu0, p.n0, pair, b0, e0);
@@ -129,6 +131,9 @@ struct NNArgs {
 // idx = argmin(d, axis=1), score = d[i, idx]   (nn_matcher.py:13-16); one warp per row.
 __global__ void __launch_bounds__(256) row_argmin_kernel(NNArgs p) {
   const int pair = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.counts[pair] = 0;   // mutual_kernel (a later launch) accumulates into it
   int b0, e0, b1, e1;
   image_range(p.cuk0, p.n0, pair, b0, e0);
   image_range(p.cuk1, p.n1, pair, b1, e1);
@@ -157,6 +162,8 @@ __global__ void __launch_bounds__(256) row_argmin_kernel(NNArgs p) {
 __global__ void __launch_bounds__(256) col_argmin_kernel(NNArgs p) {
   __shared__ float sv[8][33];
   __shared__ int si[8][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int pair = blockIdx.y;
   int b0, e0, b1, e1;
   image_range(p.cuk0, p.n0, pair, b0, e0);
@@ -187,6 +194,8 @@ __global__ void __launch_bounds__(256) col_argmin_kernel(NNArgs p) {
 
 // keep = score < thr [and i == idx2[idx[i]]]  (nn_matcher.py:18-23); counts per pair.
 __global__ void __launch_bounds__(256) mutual_kernel(NNArgs p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int pair = blockIdx.y;
   int b0, e0, b1, e1;
   image_range(p.cuk0, p.n0, pair, b0, e0);

@@ -118,9 +118,10 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
 
   if (warp == 0) {
     // ---------------------------------------------------------------- W producer: 13 slots per tile
-    if (lane == 0) {
+    {
       uint32_t it = 0;
       auto push = [&](const TcWeight& W, int nb, int kb) {
+        if (lane != 0) return;
         const int s = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         ptx::mbar_wait(&empty[s], ph ^ 1);
@@ -132,12 +133,15 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
         ++it;
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        {   // pull the NEXT tile's descriptors (the mandatory HBM read of this stage) into L2
+        {   // pull the NEXT tile's descriptors (the mandatory HBM read of this stage) into L2:
+            // one prefetch per 128-byte line, spread over the 32 lanes of this warp
           const long long nt = (long long)(tile + gridDim.x) * p.lpt * p.T;
           const long long total = (long long)p.R * p.T;
           if (nt < total) {
             const long long rows = min((long long)p.lpt * p.T, total - nt);
-            ptx::bulk_prefetch_l2(p.desc + nt * 256, (uint32_t)(rows * 1024));
+            const char* base = reinterpret_cast<const char*>(p.desc + nt * 256);
+            for (long long ln = lane; ln < rows * 8; ln += 32)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ln * 128));
           }
         }
         push(p.W3, 0, 0);

@@ -400,3 +400,36 @@ def test_gpu_tokenizer_equals_cpu_glue(cfg):
     # and the tokenised dict drives the encoder
     out = m.eval().to(DEV)(got)["line_desc"]
     assert out.shape[1] == 256 and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("L,T", [(9, 1), (5, 100), (3, 128), (40, 7)])
+def test_token_count_extremes_vs_oracle(L, T):
+    """Tiles of the fused token kernel hold floor(128 / T) whole lines: T = 1 (128 lines per tile),
+    T > 64 (one line per tile) and a T that does not divide 128."""
+    model, sd = model_for("synthetic:0:1")
+    d = syn.make_image_inputs(800 + T, L, T, (1, T))
+    got = fwd(model, d)
+    assert np.abs(got - orc.line_transformer_forward(sd, d)).max() < DESC_TOL_TIGHT
+
+
+def test_c_abi_error_paths():
+    """Errors cross the C ABI as negative return codes + ltr_last_error(), never as crashes."""
+    import ctypes as C
+    model, _ = model_for("synthetic:0:1")
+    h = model._get_handle(DEV)
+    lib = N.load()
+    d = to_dev(syn.make_image_inputs(1, 4, 21))
+    flat = lambda k, *s: d[k].reshape(4, *s).contiguous()
+    ten = [flat("sublines", 2, 2), flat("resp_sublines", 1), flat("angle_sublines", 2), flat("pnt_sublines", 21, 2),
+           flat("desc_sublines", 21, 256), flat("score_sublines", 21, 1)]
+    out = torch.empty(4 * 256, device=DEV)
+    ws = torch.empty(1024, dtype=torch.uint8, device=DEV)
+
+    def call(n_tokens=21, ws_bytes=1024, lpi=4):
+        inp = N.LtrEncodeInput(*[t.data_ptr() for t in ten], None, None, 1, 4, n_tokens, lpi, 640.0, 480.0)
+        return lib.ltr_encode(h.ptr, C.byref(inp), C.c_void_p(out.data_ptr()), None, C.c_void_p(ws.data_ptr()), ws_bytes, None)
+    assert call() == -3 and b"workspace" in lib.ltr_last_error()          # LTR_E_WORKSPACE
+    assert call(n_tokens=129) == -4                                        # LTR_E_UNSUPPORTED
+    assert call(lpi=3) == -1                                               # LTR_E_INVALID
+    with pytest.raises(N.LtrError):
+        _ops.ModelHandle({"klenc.cls_token": np.zeros(256, np.float32)}, 0)   # missing checkpoint tensors
