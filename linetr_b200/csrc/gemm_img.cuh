@@ -250,11 +250,15 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
             *reinterpret_cast<float4*>(&stg[lane * 32 + ((c4 ^ (lane & 7)) << 2)]) =
                 make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
           __syncwarp();
+          // 256-bit stores: 4 lanes cover one 128-byte row segment, 8 rows per instruction
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + (lane >> 3), c4 = lane & 7;
-            const float4 v = *reinterpret_cast<const float4*>(&stg[rl * 32 + ((c4 ^ (rl & 7)) << 2)]);
-            if (row0 + rl < p.M) *reinterpret_cast<float4*>(p.C + (long long)(row0 + rl) * p.ldc + nbase + c4 * 4) = v;
+          for (int i = 0; i < 4; ++i) {
+            const int rl = i * 8 + (lane >> 2), c8 = lane & 3;
+            const float4 v0 = *reinterpret_cast<const float4*>(&stg[rl * 32 + (((2 * c8) ^ (rl & 7)) << 2)]);
+            const float4 v1 = *reinterpret_cast<const float4*>(&stg[rl * 32 + (((2 * c8 + 1) ^ (rl & 7)) << 2)]);
+            if (row0 + rl < p.M)
+              ptx::st_global_256(p.C + (long long)(row0 + rl) * p.ldc + nbase + c8 * 8, *reinterpret_cast<const uint4*>(&v0),
+                                 *reinterpret_cast<const uint4*>(&v1));
           }
           __syncwarp();
         }
@@ -277,17 +281,27 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
           uint8_t* ohi = reinterpret_cast<uint8_t*>(p.O.hi + toff);
           uint8_t* olo = reinterpret_cast<uint8_t*>(p.O.lo + toff);
           const int gch0 = (nbase & 63) >> 3;   // first 16-byte chunk of these 32 columns inside the 64-wide k-block
+          // 256-bit stores: the 4 chunks of a row form one aligned 64-byte group of its 128-byte tile
+          // line; lane pair (2 x 32 B) per row and plane, 16 rows per instruction
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rl = i * 8 + (lane >> 2), cc = lane & 3;
+          for (int i = 0; i < 2; ++i) {
+            const int rl = i * 16 + (lane >> 1), hp = lane & 1;     // hp: which 32-byte half of the 64-byte group
             const int r_in = q * 32 + rl;
-            const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
-            const uint4 vh = *reinterpret_cast<const uint4*>(stgb + slot);
-            const uint4 vl = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
+            // physical chunk index inside the group = (gch0 + cc) ^ (r_in & 7) restricted to the group's 2 low bits
+            const int base_phys = (gch0 ^ (r_in & 7)) & 4;          // which 64-byte half of the 128-byte line
+            uint4 vh[2], vl[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int phys = hp * 2 + e;                           // physical chunk (0..3) inside the group
+              const int cc = (phys ^ (r_in & 3));                    // logical chunk stored there (low two bits of the XOR)
+              const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
+              vh[e] = *reinterpret_cast<const uint4*>(stgb + slot);
+              vl[e] = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
+            }
             if (row0 + rl < p.M) {
-              const uint32_t off = ptx::sw128_offset(r_in, (gch0 + cc) * 8);
-              *reinterpret_cast<uint4*>(ohi + off) = vh;
-              *reinterpret_cast<uint4*>(olo + off) = vl;
+              const uint32_t off = (r_in >> 3) * 1024u + (r_in & 7u) * 128u + (uint32_t)(base_phys + hp * 2) * 16u;
+              ptx::st_global_256(ohi + off, vh[0], vh[1]);
+              ptx::st_global_256(olo + off, vl[0], vl[1]);
             }
           }
           __syncwarp();
