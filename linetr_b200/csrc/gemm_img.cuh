@@ -319,24 +319,21 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
 }
 
 inline int device_sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
-  return sms;
+  return sms[dev];
 }
 
 template <int BN>
 static int launch_gemm_img_bn(GemmImgArgs a, cudaStream_t s) {
   using Cfg = GemmImgCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LTR_CUDA_TRY(cudaFuncSetAttribute(gemm_img_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr_set = true;
-  }
+  LTR_CUDA_TRY(ensure_dynamic_smem(gemm_img_kernel<BN>, Cfg::SMEM));
   a.m_tiles = cdiv(a.M, 128);
   a.n_blks = a.W.N / BN;
   const int tiles = a.m_tiles * a.n_blks;

@@ -266,12 +266,8 @@ static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const fl
                             int rows, float width, float height, cudaStream_t s) {
   if (rows <= 0) return 0;
   constexpr int IN = TOKEN ? 3 : 5;
-  static bool attr_set = false;
   const int smem = (int)sizeof(SmallMlpSmem<IN>);
-  if (!attr_set) {
-    LTR_CUDA_TRY(cudaFuncSetAttribute(small_mlp_kernel<TOKEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  LTR_CUDA_TRY(ensure_dynamic_smem(small_mlp_kernel<TOKEN>, smem));
   const int groups = cdiv(rows, SM_ROWS);
   int grid = cdiv(groups, SM_WARPS);
   if (grid > 148 * 3) grid = 148 * 3;

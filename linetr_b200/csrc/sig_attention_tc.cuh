@@ -255,11 +255,7 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
 inline int launch_sig_attention_tc(const float* qkv, ActImg out, int out_k0, const int* cu, int lpi, int max_l,
                                    int n_images, cudaStream_t s) {
   if (max_l <= 0 || n_images <= 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LTR_CUDA_TRY(cudaFuncSetAttribute(sig_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SigAttnSmem::TOTAL));
-    attr_set = true;
-  }
+  LTR_CUDA_TRY(ensure_dynamic_smem(sig_attention_tc_kernel, SigAttnSmem::TOTAL));
   dim3 grid(cdiv(max_l, 128), 4, n_images);
   LaunchScope ls(KC_SIG_ATTN, s);
   LTR_CUDA_TRY(launch_pdl(sig_attention_tc_kernel, grid, dim3(256), SigAttnSmem::TOTAL, s, qkv, out, out_k0, cu, lpi));

@@ -419,14 +419,13 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
 inline int launch_token_fused(TokenFusedArgs a, cudaStream_t s) {
   if (a.R <= 0) return 0;
   if (a.T < 1 || a.T > 128) return set_error(-1, "token_fused: T must be in 1..128");
-  static bool attr_set = false;
-  if (!attr_set) {
-    LTR_CUDA_TRY(cudaFuncSetAttribute(token_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TokenFusedSmem::TOTAL));
-    attr_set = true;
-  }
+  LTR_CUDA_TRY(ensure_dynamic_smem(token_fused_kernel, TokenFusedSmem::TOTAL));
   a.lpt = 128 / a.T;
   a.n_tiles = cdiv(a.R, a.lpt);
-  const int sms = 148;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
   LaunchScope ls(KC_TOKEN_FUSED, s);
   LTR_CUDA_TRY(launch_pdl(token_fused_kernel, dim3(grid), dim3(320), TokenFusedSmem::TOTAL, s, a));
