@@ -119,20 +119,21 @@ __device__ __forceinline__ void image_range(const int* __restrict__ cu, int lpi,
   if (cu) { b = cu[i]; e = cu[i + 1]; } else { b = i * lpi; e = b + lpi; }
 }
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device AND per kernel: remember the
+// (kernel address, device) pairs already configured.  (Kernels sharing a signature share the
+// template instantiation below, so the cache must be keyed by the function pointer.)
 template <typename K>
 inline cudaError_t ensure_dynamic_smem(K kernel, int bytes) {
-  static bool done[64] = {false};
+  static std::vector<std::pair<const void*, int>> done;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (!done[dev]) {
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    done[dev] = true;
-  }
-  return cudaSuccess;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (auto& d : done)
+    if (d.first == key && d.second == dev) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.emplace_back(key, dev);
+  return e;
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -213,7 +213,7 @@ static EncodeWs carve(const LtrModel* m, int n_lines, int T, char* base) {
   };
   auto takef = [&](int64_t floats) { return reinterpret_cast<float*>(take(floats * 4)); };
   auto takei = [&](int64_t rows, int K) {
-    const int64_t mpad = align_up(rows, 128);
+    const int64_t mpad = align_up(rows, 256);
     ActImg a;
     a.hi = reinterpret_cast<__nv_bfloat16*>(take(mpad * K * 2));
     a.lo = reinterpret_cast<__nv_bfloat16*>(take(mpad * K * 2));
@@ -716,7 +716,7 @@ int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float
   for (size_t i = 0; i < W.size(); ++i) W[i] = w_host[i];
   std::vector<uint16_t> img(2 * (size_t)n * k);
   pack_tc_weight(W.data(), n, k, img.data(), img.data() + (size_t)n * k);
-  const size_t mpad = (size_t)cdiv(m, 128) * 128;
+  const size_t mpad = (size_t)cdiv(m, 256) * 256;
   uint16_t *dw = nullptr, *da = nullptr, *dout = nullptr;
   cudaError_t ce = cudaMalloc(&dw, img.size() * 2);
   if (ce == cudaSuccess) ce = cudaMalloc(&da, 2 * mpad * k * 2);
@@ -771,7 +771,7 @@ const unsigned long long* ltr_gemm_trace(void) { return g_trace_host; }
 
 float ltr_gemm_bench(int32_t m, int32_t n, int32_t k, int32_t bn_hint, int32_t out_mode, int32_t iters, int32_t device) {
   if (cudaSetDevice(device) != cudaSuccess) return -1.f;
-  const size_t mpad = (size_t)cdiv(m, 128) * 128;
+  const size_t mpad = (size_t)cdiv(m, 256) * 256;
   uint16_t *dw = nullptr, *da = nullptr, *dout = nullptr;
   float* dc = nullptr;
   cudaMalloc(&dw, 2 * (size_t)n * k * 2);
