@@ -307,14 +307,11 @@ def shard_range(n_items: int, rank: int, world: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
-_gather_buffers = {}
-
-
 def gather_counts(local_counts: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     """The path's one collective: all-gather of per-pair match counts (int32) so that every
     rank knows the global result size.  Works with NCCL (CUDA tensors) and gloo (CPU).
-    Equal shards (the usual case) take the single-kernel `all_gather_into_tensor` path with a
-    cached output buffer; ragged shards are padded to the widest one."""
+    Equal shards (the usual case) take the single-kernel `all_gather_into_tensor` path; ragged
+    shards are padded to the widest one."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_counts.clone()
@@ -322,12 +319,8 @@ def gather_counts(local_counts: torch.Tensor, n_total: int, group=None) -> torch
     sizes = [shard_range(n_total, r, world) for r in range(world)]
     width = max(e - s for s, e in sizes)
     equal = all(e - s == width for s, e in sizes) and local_counts.numel() == width
-    key = (n_total, world, str(local_counts.device), local_counts.dtype)
-    out = _gather_buffers.get(key)
-    if out is None or out.numel() != width * world:
-        out = torch.empty(width * world, dtype=local_counts.dtype, device=local_counts.device)
-        _gather_buffers[key] = out
     if equal and local_counts.is_cuda:
+        out = torch.empty(width * world, dtype=local_counts.dtype, device=local_counts.device)   # no kernel
         dist.all_gather_into_tensor(out, local_counts.contiguous(), group=group)
         return out
     buf = torch.zeros(width, dtype=local_counts.dtype, device=local_counts.device)
