@@ -150,7 +150,7 @@ def match_descriptors(desc0, desc1, layout, n_pairs, nn_thresh, mutual=True, *, 
         "matches0": torch.empty(max(total_k0, 1), **i32)[:total_k0],
         "scores0": torch.empty(max(total_k0, 1), **f32)[:total_k0],
         "nn1": torch.empty(max(total_k1, 1), **i32)[:total_k1],
-        "counts": torch.zeros(max(n_pairs, 1), **i32)[:n_pairs],
+        "counts": (torch.zeros if n_pairs == 0 else torch.empty)(max(n_pairs, 1), **i32)[:n_pairs],   # zeroed by the kernels
         "dist_key": torch.empty(max(n_pairs * stride, 1), **f32)[:n_pairs * stride],
         "stride": stride,
     }

@@ -307,22 +307,28 @@ def shard_range(n_items: int, rank: int, world: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
-def gather_counts(local_counts: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+def gather_counts(local_counts: torch.Tensor, n_total: int, group=None, async_op: bool = False):
     """The path's one collective: all-gather of per-pair match counts (int32) so that every
     rank knows the global result size.  Works with NCCL (CUDA tensors) and gloo (CPU).
     Equal shards (the usual case) take the single-kernel `all_gather_into_tensor` path; ragged
-    shards are padded to the widest one."""
+    shards are padded to the widest one.
+
+    async_op=True (equal CUDA shards only) returns (tensor, work): the collective runs on NCCL's
+    stream behind the matcher and the caller's stream is NOT made to wait for it, so the next
+    batch's kernels overlap the gather; call work.wait() before reading the tensor."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return local_counts.clone()
+        return (local_counts.clone(), None) if async_op else local_counts.clone()
     world = dist.get_world_size(group)
     sizes = [shard_range(n_total, r, world) for r in range(world)]
     width = max(e - s for s, e in sizes)
     equal = all(e - s == width for s, e in sizes) and local_counts.numel() == width
     if equal and local_counts.is_cuda:
         out = torch.empty(width * world, dtype=local_counts.dtype, device=local_counts.device)   # no kernel
-        dist.all_gather_into_tensor(out, local_counts.contiguous(), group=group)
-        return out
+        work = dist.all_gather_into_tensor(out, local_counts.contiguous(), group=group, async_op=async_op)
+        return (out, work) if async_op else out
+    if async_op:
+        raise ValueError("gather_counts(async_op=True) needs equal CUDA shards")
     buf = torch.zeros(width, dtype=local_counts.dtype, device=local_counts.device)
     buf[:local_counts.numel()] = local_counts
     gathered = [torch.empty_like(buf) for _ in range(world)]
