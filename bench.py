@@ -62,7 +62,7 @@ def gemm_flops_per_image(L, T, n_sig=7):
     """Useful FLOPs the `linear` kernel class (gemm_img_kernel launches) is responsible for, one
     image: line stage (per-head V projection, fc, FFN, wide line-positional layers), signature
     layers (qkv, MLP with the merge projection folded in, MLP out) and final_proj.  The 3x
-    split-bf16 products and the zero blocks of the block-diagonal V projection are NOT counted."""
+    split-bf16 products are NOT counted."""
     line = 2 * (4 * 256 * 64 + 256 * 256 + 2 * 256 * 1024 + 128 * 256 + 256 * 256) * L
     sig = 2 * (256 * 768 + 512 * 512 + 512 * 256) * L * n_sig
     fin = 2 * 256 * 256 * L

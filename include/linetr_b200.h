@@ -209,8 +209,8 @@ int ltr_linear(const float* x, int32_t ldx, const float* w, const float* bias, c
  * tcgen05): x is converted to a
  * split-bf16 tile image, the GEMM writes fp32 rows into `y` (may be NULL) and - when
  * `y_from_image` is given - also the split-bf16 image of the result, which is converted back
- * to fp32 rows [m, n] there so that both outputs can be checked.  n % 128 == 0, k % 64 == 0;
- * bn_hint: 0 (auto), 128 or 256.  Synchronous; unit-test hook only. */
+ * to fp32 rows [m, n] there so that both outputs can be checked.  n % 64 == 0, k % 64 == 0;
+ * bn_hint: 0 (auto), 64, 128 or 256.  Synchronous; unit-test hook only. */
 int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float* bias,
                    const float* res, int32_t ldr, float* y, int32_t ldy, float* y_from_image,
                    int32_t m, int32_t n, int32_t k, int32_t act, int32_t bn_hint, int32_t device,

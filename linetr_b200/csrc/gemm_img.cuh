@@ -25,7 +25,8 @@
 namespace ltr {
 
 struct GemmImgArgs {
-  ActImg A; int a_kb0;       // contract k-blocks [a_kb0, a_kb0 + W.K/64) of A
+  ActImg A; int a_kb0;       // contract k-blocks [a_kb0 + nb*a_kb_nb, ... + W.K/64) of A for n-block nb
+  int a_kb_nb;               // 0 for a plain GEMM; K/64 for a block-diagonal one (each n-block reads its own K slice)
   TcWeight W;
   const float* bias;
   const float* R; int ldr;   // fp32 residual (added after the activation) or nullptr
@@ -44,7 +45,7 @@ struct GemmImgCfg {
   static constexpr int A_TILE = 16384;            // one plane of a 128x64 bf16 tile
   static constexpr int W_TILE = BN * 128;         // one plane of a BN x 64 bf16 tile
   static constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
-  static constexpr int STAGES = BN >= 256 ? 2 : 3;
+  static constexpr int STAGES = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
   static constexpr int STG_WARP = 4096;           // per epilogue warp: 32 rows x 32 fp32 (or 2 x [32 x 64 B] bf16)
   static constexpr int OFF_STG = STAGES * STAGE;
   static constexpr int OFF_BAR = OFF_STG + 8 * STG_WARP;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
           if (it < 4) LTR_STAMP(it * 16 + 6);
           uint8_t* st = smem + s * Cfg::STAGE;
-          const size_t aoff = ((size_t)mt * p.A.kblocks + p.a_kb0 + kb) * IMG_TILE_ELEMS;
+          const size_t aoff = ((size_t)mt * p.A.kblocks + p.a_kb0 + nb * p.a_kb_nb + kb) * IMG_TILE_ELEMS;
           const size_t woff = ((size_t)kb * (p.W.N / 8) + (size_t)nb * (BN / 8)) * 1024;
           ptx::mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
           ptx::bulk_g2s(st, p.A.hi + aoff, Cfg::A_TILE, &full[s]);
@@ -346,8 +347,9 @@ static int launch_gemm_img_bn(GemmImgArgs a, cudaStream_t s) {
 // bn_hint: 0 = choose (256 when N % 256 == 0 and that still gives >= 1 tile per SM, else 128)
 inline int launch_gemm_img(const GemmImgArgs& a, cudaStream_t s, int bn_hint = 0) {
   if (a.M <= 0) return 0;
-  if (a.W.K % 64 || a.W.N % 128 || (a.C && a.ldc % 4) || (a.R && a.ldr % 4))
-    return set_error(-1, "gemm_img: K%64, N%128, ld%4 required");
+  if (a.W.K % 64 || a.W.N % 64 || (a.C && a.ldc % 8) || (a.R && a.ldr % 4))
+    return set_error(-1, "gemm_img: K%64, N%64, ldc%8, ldr%4 required");
+  if (bn_hint == 64 || a.W.N % 128) return launch_gemm_img_bn<64>(a, s);
   int bn = bn_hint;
   if (!bn) {
     bn = 128;

@@ -252,13 +252,13 @@ static LinearArgs lin(const float* A, int lda, const float* W, const float* b, f
 // (optional) and/or image O k-blocks from o_kb0 (optional); R = fp32 residual.
 static int gemm(const Lin& L, const ActImg& A, int a_kb0, int M, int act, cudaStream_t s, float* C, int ldc,
                 const ActImg* O = nullptr, int o_kb0 = 0, const float* R = nullptr, int ldr = 0,
-                const ActImg* Rimg = nullptr, int r_kb0 = 0) {
+                const ActImg* Rimg = nullptr, int r_kb0 = 0, int bn_hint = 0, int a_kb_nb = 0) {
   GemmImgArgs a{};
   a.A = A; a.a_kb0 = a_kb0; a.W = L.tw; a.bias = L.b; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc;
   if (O) { a.O = *O; a.o_kb0 = o_kb0; }
   if (Rimg) { a.Rimg = *Rimg; a.r_kb0 = r_kb0; }
-  a.M = M; a.act = act;
-  return launch_gemm_img(a, s);
+  a.M = M; a.act = act; a.a_kb_nb = a_kb_nb;
+  return launch_gemm_img(a, s, bn_hint);
 }
 
 template <bool TOKEN>
@@ -311,7 +311,7 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
     LTR_TRY(launch_token_fused(a, s));
   }
   // ---- line stage: V projection (block diagonal over heads), fc + CLS residual, LN, FFN, LN, + line pos ----
-  LTR_TRY(gemm(m->wv, w.z, 0, R, ACT_NONE, s, nullptr, 0, &w.ctx, 0));
+  LTR_TRY(gemm(m->wv, w.z, 0, R, ACT_NONE, s, nullptr, 0, &w.ctx, 0, nullptr, 0, nullptr, 0, 64, 4));
   LTR_TRY(gemm(m->wfc, w.ctx, 0, R, ACT_NONE, s, w.y1pre, 256));
   LTR_TRY(launch_layernorm(w.y1pre, 256, m->ln1g, m->ln1b, nullptr, 0, w.y1, 256, w.y1i, 0, R, s));
   LTR_TRY(gemm(m->w1, w.y1i, 0, R, ACT_GELU, s, nullptr, 0, &w.g, 0));
@@ -463,13 +463,10 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   std::vector<double> bfc_cls(D);
   for (int i = 0; i < D; ++i) bfc_cls[i] = (double)bfc[i] + cls[i];  // fc bias + CLS residual (line_attention.py:72)
   size_t oU = hp.add(U), oS = hp.add(scls), oC = hp.add(vec(cls, D));
-  // V projection of the pooled per-head inputs z = [z_0 | z_1 | z_2 | z_3] (K = 4*256) as one
-  // block-diagonal [256, 1024] matrix: output channel h*64+d only sees z_h.
-  std::vector<double> Wvbd((size_t)D * 4 * D, 0.0);
-  for (int h = 0; h < 4; ++h)
-    for (int d = 0; d < 64; ++d)
-      for (int c = 0; c < D; ++c) Wvbd[(size_t)(h * 64 + d) * (4 * D) + h * D + c] = wv[(h * 64 + d) * D + c];
-  LinOff oWv = hp.add_lin(Wvbd, vec(bv, D), D, 4 * D);
+  // V projection of the pooled per-head inputs z = [z_0 | z_1 | z_2 | z_3]: output channels h*64..h*64+63
+  // only see z_h, i.e. a block-diagonal GEMM - run as N = 256, K = 256 with 64-wide n-blocks whose A
+  // k-blocks start at 4*h (GemmImgArgs::a_kb_nb).
+  LinOff oWv = hp.add_lin(vec(wv, D * D), vec(bv, D), D, D);
   LinOff oWfc = hp.add_lin(vec(wfc, D * D), bfc_cls, D, D);
   size_t oL1g = hp.add(vec(ln1g, D)), oL1b = hp.add(vec(ln1b, D));
   LinOff oW1 = hp.add_lin(vec(w1, (size_t)DI * D), vec(b1, DI), DI, D);
@@ -709,7 +706,7 @@ int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float
                    float* y, int32_t ldy, float* y_from_image, int32_t m, int32_t n, int32_t k, int32_t act,
                    int32_t bn_hint, int32_t device, void* stream) {
   if (!x || !w_host || (!y && !y_from_image)) return set_error(LTR_E_INVALID, "ltr_linear_img: null argument");
-  if (n % 128 || k % 64) return set_error(LTR_E_UNSUPPORTED, "ltr_linear_img: n %% 128 and k %% 64 required");
+  if (n % 64 || k % 64) return set_error(LTR_E_UNSUPPORTED, "ltr_linear_img: n and k must be multiples of 64");
   LTR_CUDA_TRY(cudaSetDevice(device));
   cudaStream_t s = as_stream(stream);
   std::vector<double> W((size_t)n * k);

@@ -63,7 +63,8 @@ def test_linear_engine_vs_torch_fp32(M, N_, K, act):
 
 @pytest.mark.parametrize("M,N_,K,act,bn", [(1, 128, 64, 0, 0), (128, 128, 64, 0, 128), (127, 256, 128, 1, 256),
                                            (300, 768, 256, 0, 256), (513, 1024, 256, 2, 0), (64, 256, 1024, 0, 128),
-                                           (40000, 256, 256, 0, 256), (20000, 512, 512, 1, 0), (1000, 256, 512, 0, 128)])
+                                           (40000, 256, 256, 0, 256), (20000, 512, 512, 1, 0), (1000, 256, 512, 0, 128),
+                                           (700, 64, 128, 1, 64), (3000, 192, 256, 0, 0), (20000, 256, 256, 2, 64)])
 def test_persistent_image_gemm_vs_fp64(M, N_, K, act, bn):
     """gemm_img engine: TMA-fed split-bf16 tile images in, fp32 rows + split-bf16 image out,
     persistent CTAs with double-buffered TMEM accumulators (more tiles than SMs at M=40000)."""
