@@ -315,6 +315,22 @@ def main():
                     "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json); useful FLOPs only",
                     "launches_per_step": dom_launches / args.steps, "avg_launch_ms": avg_ms,
                     "algorithmic_flops_per_launch": per_launch_flops}
+        # secondary rooflines (same live per-class times): the attention kernels the metric names
+        # ("attn roofline %") against the tensor peak, and the token stage against HBM - its one
+        # mandatory stream is the sampled descriptors, everything else stays on chip.
+        by_class = {}
+        for name in ("sig_attention", "token_fused", "linear"):
+            if name in prof and prof[name][1]:
+                ms_c, n_c = prof[name]
+                tf = class_flops[name] * args.steps / (ms_c * 1e-3) / 1e12
+                by_class[name] = {"kernel": class_kernel[name], "launches_per_step": n_c / args.steps,
+                                  "avg_launch_ms": ms_c / n_c, "useful_tflops": tf,
+                                  "frac_tensor_peak": tf / peaks["bf16_tflops_sustained"]}
+        if "token_fused" in by_class:
+            tok_bytes = 2 * P * bytes_per_image(L, T) - 2 * P * 4 * 256 * L + 2 * P * 4 * 1024 * L   # inputs + z image (hi/lo bf16)
+            gbs = tok_bytes * args.steps / (prof["token_fused"][0] * 1e-3) / 1e9
+            by_class["token_fused"].update({"algorithmic_bytes_per_launch": tok_bytes * args.steps / prof["token_fused"][1],
+                                            "hbm_gbs": gbs, "frac_hbm_peak": gbs / peaks["hbm_gbs"]})
         cpu_v, cpu_n, cores, note = cpu_reference_pairs_per_s(L, T, args.cpu_budget)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -327,6 +343,7 @@ def main():
                "useful_tflops": useful_flops_step / (ms_step * 1e-3) / 1e12,
                "hbm_gbs_algorithmic": (2 * P * bytes_per_image(L, T) + 8 * P * L) / (ms_step * 1e-3) / 1e9,
                "kernel_time_shares": shares,
+               "roofline_by_class": by_class,
                "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{cpu_n} pairs of {L}x{T}, B=1 per call; {note}"}}
         print(json.dumps(out))

@@ -56,8 +56,8 @@ struct TokenFusedSmem {
   static constexpr int OFF_U = OFF_B5 + 256 * 4;           // 1024
   static constexpr int OFF_CLS = OFF_U + 1024 * 4;         // 256
   static constexpr int OFF_SC = OFF_CLS + 256 * 4;         // partial scores [2][128][4]
-  static constexpr int OFF_P = OFF_SC + 2 * 128 * 4 * 4;   // probabilities [128][4] + cls [lpt <= 128][4]
-  static constexpr int OFF_BAR = OFF_P + (128 + 128) * 4 * 4;
+  static constexpr int OFF_P = OFF_SC + 2 * 128 * 4 * 4;   // softmax scratch (see below)
+  static constexpr int OFF_BAR = OFF_P + (512 + 512 + 512) * 4;   // exps [128][4], 1/sum [<=512], CLS exp [<=512]
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;       // + alignment slack
 };
 
@@ -366,44 +366,67 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       if (tr) LTR_DBG_STAMP(7);
       worker_sync();
       if (tr) LTR_DBG_STAMP(8);
-      // ---- softmax over the T tokens + CLS of every (line, head): threads 0 .. 4*lpt-1
+      // ---- softmax over the T tokens + CLS of every (line, head), spread over the row threads:
+      //      (1) combine the two column halves of the scores, (2) per (line, head) maximum,
+      //      (3) one exp per (row, head), (4) per (line, head) sum -> 1/sum and the CLS weight.
+      //      sP keeps UNNORMALISED exps; the pooling multiplies by 1/sum once per output.
+      float* sM = sSc + 512;      // [4*lpt] maxima   (second half of the partial-score buffer, dead after (1))
+      float* sInv = sP + 512;     // [4*lpt] 1/sum;   sP + 1024 .. : [4*lpt] CLS weight e0
+      if (wt < 128) {
+        const float4 a = *reinterpret_cast<const float4*>(&sSc[wt * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&sSc[(128 + wt) * 4]);
+        *reinterpret_cast<float4*>(&sP[wt * 4]) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+      worker_sync();
       for (int pi = wt; pi < 4 * p.lpt; pi += 256) {
-        const int ln = pi >> 2, h = pi & 3;
-        const int rb = ln * p.T;
+        const int ln = pi >> 2, h = pi & 3, rb = ln * p.T;
         float m = p.s_cls[h];
-        for (int n = 0; n < p.T; ++n) m = fmaxf(m, sSc[(rb + n) * 4 + h] + sSc[(128 + rb + n) * 4 + h]);
-        float e0 = expf(p.s_cls[h] - m), sum = e0;
-        for (int n = 0; n < p.T; ++n) {
-          const float e = expf(sSc[(rb + n) * 4 + h] + sSc[(128 + rb + n) * 4 + h] - m);
-          sP[(rb + n) * 4 + h] = e;
-          sum += e;
-        }
-        const float inv = 1.f / sum;
-        for (int n = 0; n < p.T; ++n) sP[(rb + n) * 4 + h] *= inv;
-        sP[(128 + ln) * 4 + h] = e0 * inv;
+        for (int n = 0; n < p.T; ++n) m = fmaxf(m, sP[(rb + n) * 4 + h]);
+        sM[pi] = m;
+      }
+      worker_sync();
+      if (wt < rows_used) {
+        const int ln = wt / p.T;
+        float4 v = *reinterpret_cast<const float4*>(&sP[wt * 4]);
+        v.x = expf(v.x - sM[ln * 4 + 0]);
+        v.y = expf(v.y - sM[ln * 4 + 1]);
+        v.z = expf(v.z - sM[ln * 4 + 2]);
+        v.w = expf(v.w - sM[ln * 4 + 3]);
+        *reinterpret_cast<float4*>(&sP[wt * 4]) = v;
+      }
+      worker_sync();
+      for (int pi = wt; pi < 4 * p.lpt; pi += 256) {
+        const int ln = pi >> 2, h = pi & 3, rb = ln * p.T;
+        const float e0 = expf(p.s_cls[h] - sM[pi]);
+        float sum = e0;
+        for (int n = 0; n < p.T; ++n) sum += sP[(rb + n) * 4 + h];
+        sInv[pi] = 1.f / sum;
+        sP[1024 + pi] = e0;
       }
       worker_sync();
       if (tr) LTR_DBG_STAMP(9);
-      // ---- pooling: thread = channel; z_h[c] = p_cls * cls[c] + sum_n p[n] x[n][c]
+      // ---- pooling: thread = channel; z_h[c] = (e0 * cls[c] + sum_n e[n] x[n][c]) / sum
       {
         const int c = wt;
         const float cv = sCls[c];
         for (int ln = 0; ln < p.lpt; ++ln) {
           const int gl = line0 + ln;
           if (gl >= p.R) break;
-          const float4 pc = *reinterpret_cast<const float4*>(&sP[(128 + ln) * 4]);
+          const float4 pc = *reinterpret_cast<const float4*>(&sP[1024 + ln * 4]);
           float z0 = pc.x * cv, z1 = pc.y * cv, z2 = pc.z * cv, z3 = pc.w * cv;
           const int rb = ln * p.T;
+#pragma unroll 7
           for (int n = 0; n < p.T; ++n) {
             const float xv = xs[xs_index(rb + n, c)];
             const float4 pr = *reinterpret_cast<const float4*>(&sP[(rb + n) * 4]);
             z0 = fmaf(pr.x, xv, z0); z1 = fmaf(pr.y, xv, z1);
             z2 = fmaf(pr.z, xv, z2); z3 = fmaf(pr.w, xv, z3);
           }
-          img_store1(p.z, gl, c, z0);
-          img_store1(p.z, gl, 256 + c, z1);
-          img_store1(p.z, gl, 512 + c, z2);
-          img_store1(p.z, gl, 768 + c, z3);
+          const float4 iv = *reinterpret_cast<const float4*>(&sInv[ln * 4]);
+          img_store1(p.z, gl, c, z0 * iv.x);
+          img_store1(p.z, gl, 256 + c, z1 * iv.y);
+          img_store1(p.z, gl, 512 + c, z2 * iv.z);
+          img_store1(p.z, gl, 768 + c, z3 * iv.w);
         }
       }
       if (tr) LTR_DBG_STAMP(10);
