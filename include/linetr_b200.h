@@ -216,6 +216,16 @@ int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float
                    int32_t m, int32_t n, int32_t k, int32_t act, int32_t bn_hint, int32_t device,
                    void* stream);
 
+/* ltr_linear_img with the row-normalising epilogue the encoder uses (n = 256 fixed): norm = 1:
+ * y = LayerNorm(x W^T + b (+ res); eps) * gamma + beta (+ add)   - MultiHeadAttention / FeedForward
+ * tails, models/line_attention.py:51-53,73-75, plus the `klines_pos +` of models/line_transformer.py:128;
+ * norm = 2: y = (x W^T + b) / max(||.||_2, 1e-12)               - final_proj + F.normalize,
+ * models/line_transformer.py:245-246.  Synchronous; unit-test hook only. */
+int ltr_linear_img_norm(const float* x, int32_t ldx, const float* w_host, const float* bias,
+                        const float* res, int32_t ldr, int32_t norm, float eps, const float* gamma,
+                        const float* beta, const float* add, int32_t ldadd, float* y, int32_t ldy,
+                        float* y_from_image, int32_t m, int32_t k, int32_t device, void* stream);
+
 /* Micro-benchmark of the image-operand GEMM engine (zero-filled operands, timing only):
  * average device milliseconds per launch.  out_mode: 0 fp32 rows, 1 image, 2 both. */
 float ltr_gemm_bench(int32_t m, int32_t n, int32_t k, int32_t bn_hint, int32_t out_mode, int32_t iters,

@@ -21,7 +21,7 @@ LAYOUT_CHANNEL_FIRST = 1
 # Every symbol include/linetr_b200.h declares (tests check the library exports all of them).
 EXPORTED_SYMBOLS = (
     "ltr_abi_version", "ltr_last_error", "ltr_create", "ltr_destroy", "ltr_encode_workspace_bytes",
-    "ltr_encode", "ltr_match", "ltr_match_distmat", "ltr_merge_sublines", "ltr_tokenize", "ltr_linear", "ltr_linear_img", "ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read", "ltr_launch_count",
+    "ltr_encode", "ltr_match", "ltr_match_distmat", "ltr_merge_sublines", "ltr_tokenize", "ltr_linear", "ltr_linear_img", "ltr_linear_img_norm", "ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read", "ltr_launch_count",
     "ltr_reset_launch_count", "ltr_profile_begin", "ltr_profile_end",
 )
 
@@ -115,6 +115,10 @@ def load():
                                    C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p]
     lib.ltr_linear_img.restype = C.c_int
+    lib.ltr_linear_img_norm.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                        C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.ltr_linear_img_norm.restype = C.c_int
     lib.ltr_gemm_bench.argtypes = [C.c_int32] * 7
     lib.ltr_gemm_bench.restype = C.c_float
     lib.ltr_gemm_trace.restype = C.POINTER(C.c_uint64)

@@ -62,7 +62,7 @@ class ModelHandle:
         self._lib = lib
         self.ptr = h
         self.device_index = int(device_index)
-        self._ws = None
+        self._ws = {}   # one workspace per CUDA stream: calls on one stream are ordered, streams may overlap
 
     def close(self):
         if getattr(self, "ptr", None):
@@ -79,9 +79,12 @@ class ModelHandle:
         need = int(self._lib.ltr_encode_workspace_bytes(self.ptr, n_images, n_lines, n_tokens))
         if need < 0:
             N.check(need, "ltr_encode_workspace_bytes")
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=torch.device("cuda", self.device_index))
-        return self._ws
+        dev = torch.device("cuda", self.device_index)
+        key = torch.cuda.current_stream(dev).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._ws[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+        return ws
 
 
 def encode(handle: ModelHandle, sublines, resp, angle, pnt, desc, score, image_wh, *, lines_per_image=None,
@@ -226,4 +229,25 @@ def linear_img(x: torch.Tensor, w: torch.Tensor, bias=None, res=None, act=0, bn_
         rc = N.load().ltr_linear_img(_ptr(x), K, _ptr(w), _ptr(bias), _ptr(res), Nn, _ptr(y), Nn, _ptr(y2), M, Nn, K,
                                      int(act), int(bn_hint), x.device.index, _stream_ptr(x.device))
     N.check(rc, "ltr_linear_img")
+    return y, y2
+
+
+def linear_img_norm(x: torch.Tensor, w: torch.Tensor, bias=None, res=None, norm=1, eps=1e-6, gamma=None, beta=None, add=None):
+    """ltr_linear_img_norm (unit-test hook of the row-normalising GEMM epilogue, N = 256):
+    returns (y_fp32, y_from_image)."""
+    _req_cuda(x, "x")
+    x = _f32c(x)
+    w = _f32c(w).cpu()
+    M, K = x.shape
+    if w.shape[0] != 256:
+        raise N.LtrError("linear_img_norm: the row-norm epilogue is built for N = 256")
+    y = torch.empty((M, 256), dtype=torch.float32, device=x.device)
+    y2 = torch.empty((M, 256), dtype=torch.float32, device=x.device)
+    f = lambda t: _f32c(t) if t is not None else None
+    bias, res, gamma, beta, add = map(f, (bias, res, gamma, beta, add))
+    with torch.cuda.device(x.device):
+        rc = N.load().ltr_linear_img_norm(_ptr(x), K, _ptr(w), _ptr(bias), _ptr(res), 256, int(norm), float(eps), _ptr(gamma),
+                                          _ptr(beta), _ptr(add), 256, _ptr(y), 256, _ptr(y2), M, K, x.device.index,
+                                          _stream_ptr(x.device))
+    N.check(rc, "ltr_linear_img_norm")
     return y, y2

@@ -34,9 +34,17 @@ struct GemmImgArgs {
   float* C; int ldc;         // fp32 output or nullptr
   ActImg O; int o_kb0;       // image output (O.hi == nullptr: none); column n -> k-block o_kb0 + n/64
   int M, act;
+  // row-normalising epilogue (BN = 256 = N only, one tile spans whole rows):
+  //   NORM_LAYER: y = LayerNorm(acc + bias (+ R)) * ng + nbeta (+ nadd)      (models/line_attention.py:51-53,73-75)
+  //   NORM_L2:    y = (acc + bias) / max(||.||_2, 1e-12)                      (models/line_transformer.py:246)
+  int norm; float eps;
+  const float* ng; const float* nbeta;
+  const float* nadd; int ldadd;   // fp32 rows added AFTER the normalisation or nullptr
   int m_tiles, n_blks;
   unsigned long long* trace;   // debug: clock64 stamps of CTA 0 (nullptr = off)
 };
+
+enum { NORM_NONE = 0, NORM_LAYER = 1, NORM_L2 = 2 };
 
 #define LTR_STAMP(slot) do { if (p.trace && blockIdx.x == 0) p.trace[slot] = clock64(); } while (0)
 
@@ -49,10 +57,190 @@ struct GemmImgCfg {
   static constexpr int STG_WARP = 4096;           // per epilogue warp: 32 rows x 32 fp32 (or 2 x [32 x 64 B] bf16)
   static constexpr int OFF_STG = STAGES * STAGE;
   static constexpr int OFF_BAR = OFF_STG + 8 * STG_WARP;
-  static constexpr int SMEM = OFF_BAR + 256 + 1024;
+  static constexpr int OFF_XCH = OFF_BAR + 256;                     // row-norm partial sums [2][2][128] fp32 (BN = 256 only)
+  static constexpr int XCH = BN == 256 ? 2048 : 0;
+  // 227 KB is the CTA limit: with the exchange buffer the BN = 256 variant keeps 768 B of alignment
+  // slack (the dynamic window starts 1024-aligned in practice; a larger pad would fault loudly)
+  static constexpr int SMEM = OFF_XCH + XCH + (BN == 256 ? 768 : 1024);
   static constexpr int TMEM_COLS = 2 * BN;        // two accumulators
   static constexpr int THREADS = 320;             // TMA warp, MMA warp, 8 epilogue warps
 };
+
+
+// ---------------------------------------------------------------- epilogue building blocks
+// One epilogue warp owns 32 accumulator rows (row0 .. row0+31, lane = row) and works on 32-column
+// chunks `acc[32]` starting at global column `nbase`.  Global traffic goes through the warp's 4 KB
+// staging tile so that each load/store instruction touches whole 32-byte sectors of a few rows.
+
+// acc += X[row0 + lane][nbase .. nbase+32) for fp32 rows X (coalesced read of the 32 x 32 tile)
+__device__ __forceinline__ void epi_add_rows_f32(const float* __restrict__ X, int ldx, int row0, int nbase, int M, int lane,
+                                                 float* stg, float (&acc)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = i * 4 + (lane >> 3), c4 = lane & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + rl < M) v = *reinterpret_cast<const float4*>(X + (long long)(row0 + rl) * ldx + nbase + c4 * 4);
+    *reinterpret_cast<float4*>(&stg[rl * 32 + ((c4 ^ (rl & 7)) << 2)]) = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float4 v = *reinterpret_cast<const float4*>(&stg[lane * 32 + ((c4 ^ (lane & 7)) << 2)]);
+    acc[c4 * 4] += v.x; acc[c4 * 4 + 1] += v.y; acc[c4 * 4 + 2] += v.z; acc[c4 * 4 + 3] += v.w;
+  }
+  __syncwarp();
+}
+
+// C[row0 + lane][nbase .. nbase+32) = acc, 256-bit stores: 4 lanes cover one 128-byte row segment
+__device__ __forceinline__ void epi_store_rows_f32(float* __restrict__ C, int ldc, int row0, int nbase, int M, int lane,
+                                                   float* stg, const float (&acc)[32]) {
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4)
+    *reinterpret_cast<float4*>(&stg[lane * 32 + ((c4 ^ (lane & 7)) << 2)]) =
+        make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = i * 8 + (lane >> 2), c8 = lane & 3;
+    const float4 v0 = *reinterpret_cast<const float4*>(&stg[rl * 32 + (((2 * c8) ^ (rl & 7)) << 2)]);
+    const float4 v1 = *reinterpret_cast<const float4*>(&stg[rl * 32 + (((2 * c8 + 1) ^ (rl & 7)) << 2)]);
+    if (row0 + rl < M)
+      ptx::st_global_256(C + (long long)(row0 + rl) * ldc + nbase + c8 * 8, *reinterpret_cast<const uint4*>(&v0),
+                         *reinterpret_cast<const uint4*>(&v1));
+  }
+  __syncwarp();
+}
+
+// image O, m-tile mt, k-block kb0 + nbase/64: columns nbase .. nbase+32 of rows q*32 + lane <- split-bf16(acc)
+__device__ __forceinline__ void epi_store_image(const ActImg& O, int kb0, int mt, int nbase, int q, int row0, int M, int lane,
+                                                uint8_t* stgb, const float (&acc)[32]) {
+  // staging: plane [32 rows][4 chunks of 16 B], chunk slot swizzled by (row>>1)&3
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ptx::split_bf16(acc[cc * 8 + e], h[e], l[e]);
+    const int slot = (lane * 4 + (cc ^ ((lane >> 1) & 3))) * 16;
+    *reinterpret_cast<uint4*>(stgb + slot) =
+        make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
+    *reinterpret_cast<uint4*>(stgb + 2048 + slot) =
+        make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+  }
+  __syncwarp();
+  const int kb_out = kb0 + (nbase >> 6);
+  const size_t toff = ((size_t)mt * O.kblocks + kb_out) * IMG_TILE_ELEMS;
+  uint8_t* ohi = reinterpret_cast<uint8_t*>(O.hi + toff);
+  uint8_t* olo = reinterpret_cast<uint8_t*>(O.lo + toff);
+  const int gch0 = (nbase & 63) >> 3;   // first 16-byte chunk of these 32 columns inside the 64-wide k-block
+  // 256-bit stores: the 4 chunks of a row form one aligned 64-byte group of its 128-byte tile
+  // line; lane pair (2 x 32 B) per row and plane, 16 rows per instruction
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int rl = i * 16 + (lane >> 1), hp = lane & 1;     // hp: which 32-byte half of the 64-byte group
+    const int r_in = q * 32 + rl;
+    // physical chunk index inside the group = (gch0 + cc) ^ (r_in & 7) restricted to the group's 2 low bits
+    const int base_phys = (gch0 ^ (r_in & 7)) & 4;          // which 64-byte half of the 128-byte line
+    uint4 vh[2], vl[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int phys = hp * 2 + e;                           // physical chunk (0..3) inside the group
+      const int cc = (phys ^ (r_in & 3));                    // logical chunk stored there (low two bits of the XOR)
+      const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
+      vh[e] = *reinterpret_cast<const uint4*>(stgb + slot);
+      vl[e] = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
+    }
+    if (row0 + rl < M) {
+      const uint32_t off = (r_in >> 3) * 1024u + (r_in & 7u) * 128u + (uint32_t)(base_phys + hp * 2) * 16u;
+      ptx::st_global_256(ohi + off, vh[0], vh[1]);
+      ptx::st_global_256(olo + off, vl[0], vl[1]);
+    }
+  }
+  __syncwarp();
+}
+
+// barrier over the 8 epilogue warps only (the TMA and MMA warps never join it)
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Row-normalising epilogue of one 128 x 256 tile (see GemmImgArgs::norm).  A row's 256 columns sit
+// in two threads (column halves, different warps); partial sums are exchanged through `xch`.
+// The accumulator is re-read from TMEM for every pass (cheap) instead of being held in registers.
+__device__ __forceinline__ void epi_norm_tile(const GemmImgArgs& p, uint32_t tmem_acc, int mt, int q, int half, int lane,
+                                              uint32_t tl, float* stg, uint8_t* stgb, float* xch) {
+  const int row0 = mt * 128 + q * 32, r_in = q * 32 + lane, cbeg = half * 128;
+  auto chunk = [&](int c0, float (&v)[32]) {
+    ptx::tmem_ld32(tmem_acc + (uint32_t)c0, v);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + c0 + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (p.R) epi_add_rows_f32(p.R, p.ldr, row0, c0, p.M, lane, stg, v);
+  };
+  float mean = 0.f, scale;
+  if (p.norm == NORM_LAYER) {
+    float s = 0.f;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+      float v[32];
+      chunk(c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s += v[j];
+    }
+    xch[half * 128 + r_in] = s;
+    epi_bar();
+    mean = (s + xch[(half ^ 1) * 128 + r_in]) * (1.f / 256.f);
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+      float v[32];
+      chunk(c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; ss = fmaf(d, d, ss); }
+    }
+    xch[256 + half * 128 + r_in] = ss;
+    epi_bar();
+    ss += xch[256 + (half ^ 1) * 128 + r_in];
+    scale = 1.f / sqrtf(ss * (1.f / 256.f) + p.eps);
+  } else {
+    float* x = xch + (tl & 1) * 256;   // alternate slots: one barrier per tile is enough
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+      float v[32];
+      chunk(c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+    }
+    x[half * 128 + r_in] = ss;
+    epi_bar();
+    ss += x[(half ^ 1) * 128 + r_in];
+    scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+#pragma unroll 1
+  for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+    float v[32];
+    chunk(c0, v);
+    if (p.norm == NORM_LAYER) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(p.ng + c0 + j);
+        const float4 b = *reinterpret_cast<const float4*>(p.nbeta + c0 + j);
+        v[j] = (v[j] - mean) * scale * g.x + b.x;
+        v[j + 1] = (v[j + 1] - mean) * scale * g.y + b.y;
+        v[j + 2] = (v[j + 2] - mean) * scale * g.z + b.z;
+        v[j + 3] = (v[j + 3] - mean) * scale * g.w + b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= scale;
+    }
+    if (p.nadd) epi_add_rows_f32(p.nadd, p.ldadd, row0, c0, p.M, lane, stg, v);
+    if (p.C) epi_store_rows_f32(p.C, p.ldc, row0, c0, p.M, lane, stg, v);
+    if (p.O.hi) epi_store_image(p.O, p.o_kb0, mt, c0, q, row0, p.M, lane, stgb, v);
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
@@ -60,6 +248,7 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  if (BN == 256 && ((1024u - (raw & 1023u)) & 1023u) > 768u) __trap();   // see GemmImgCfg::SMEM
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
@@ -172,6 +361,16 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
       ptx::tc_fence_after();
       if (tl < 4 && warp == 2 && lane == 0) LTR_STAMP(tl * 16 + 3);
       const int row0 = mt * 128 + q * 32;   // first row of this warp
+      if constexpr (BN == 256) {
+        if (p.norm != NORM_NONE) {
+          epi_norm_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN, mt, q, half, lane, tl, stg, stgb,
+                        reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         float acc[32];
@@ -194,23 +393,7 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = 0.5f * acc[j] * (1.f + erff(acc[j] * 0.70710678118654752440f));
         }
-        if (p.R) {
-          // coalesced read of the 32 x 32 residual tile: lane -> (row i*4 + lane/8, float4 lane%8)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + (lane >> 3), c4 = lane & 7;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + rl < p.M) v = *reinterpret_cast<const float4*>(p.R + (long long)(row0 + rl) * p.ldr + nbase + c4 * 4);
-            *reinterpret_cast<float4*>(&stg[rl * 32 + ((c4 ^ (rl & 7)) << 2)]) = v;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 v = *reinterpret_cast<const float4*>(&stg[lane * 32 + ((c4 ^ (lane & 7)) << 2)]);
-            acc[c4 * 4] += v.x; acc[c4 * 4 + 1] += v.y; acc[c4 * 4 + 2] += v.z; acc[c4 * 4 + 3] += v.w;
-          }
-          __syncwarp();
-        }
+        if (p.R) epi_add_rows_f32(p.R, p.ldr, row0, nbase, p.M, lane, stg, acc);
         if (p.Rimg.hi) {
           // residual from a split-bf16 image: coalesced 16-byte chunk loads -> staging -> own row
           const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
@@ -245,68 +428,8 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
           }
           __syncwarp();
         }
-        if (p.C) {
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            *reinterpret_cast<float4*>(&stg[lane * 32 + ((c4 ^ (lane & 7)) << 2)]) =
-                make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
-          __syncwarp();
-          // 256-bit stores: 4 lanes cover one 128-byte row segment, 8 rows per instruction
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rl = i * 8 + (lane >> 2), c8 = lane & 3;
-            const float4 v0 = *reinterpret_cast<const float4*>(&stg[rl * 32 + (((2 * c8) ^ (rl & 7)) << 2)]);
-            const float4 v1 = *reinterpret_cast<const float4*>(&stg[rl * 32 + (((2 * c8 + 1) ^ (rl & 7)) << 2)]);
-            if (row0 + rl < p.M)
-              ptx::st_global_256(p.C + (long long)(row0 + rl) * p.ldc + nbase + c8 * 8, *reinterpret_cast<const uint4*>(&v0),
-                                 *reinterpret_cast<const uint4*>(&v1));
-          }
-          __syncwarp();
-        }
-        if (p.O.hi) {
-          // split to bf16 hi/lo; staging: plane [32 rows][4 chunks of 16 B], chunk slot swizzled by (row>>1)&3
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            __nv_bfloat16 h[8], l[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ptx::split_bf16(acc[cc * 8 + e], h[e], l[e]);
-            const int slot = (lane * 4 + (cc ^ ((lane >> 1) & 3))) * 16;
-            *reinterpret_cast<uint4*>(stgb + slot) =
-                make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
-            *reinterpret_cast<uint4*>(stgb + 2048 + slot) =
-                make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
-          }
-          __syncwarp();
-          const int kb_out = p.o_kb0 + (nbase >> 6);
-          const size_t toff = ((size_t)mt * p.O.kblocks + kb_out) * IMG_TILE_ELEMS;
-          uint8_t* ohi = reinterpret_cast<uint8_t*>(p.O.hi + toff);
-          uint8_t* olo = reinterpret_cast<uint8_t*>(p.O.lo + toff);
-          const int gch0 = (nbase & 63) >> 3;   // first 16-byte chunk of these 32 columns inside the 64-wide k-block
-          // 256-bit stores: the 4 chunks of a row form one aligned 64-byte group of its 128-byte tile
-          // line; lane pair (2 x 32 B) per row and plane, 16 rows per instruction
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int rl = i * 16 + (lane >> 1), hp = lane & 1;     // hp: which 32-byte half of the 64-byte group
-            const int r_in = q * 32 + rl;
-            // physical chunk index inside the group = (gch0 + cc) ^ (r_in & 7) restricted to the group's 2 low bits
-            const int base_phys = (gch0 ^ (r_in & 7)) & 4;          // which 64-byte half of the 128-byte line
-            uint4 vh[2], vl[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int phys = hp * 2 + e;                           // physical chunk (0..3) inside the group
-              const int cc = (phys ^ (r_in & 3));                    // logical chunk stored there (low two bits of the XOR)
-              const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
-              vh[e] = *reinterpret_cast<const uint4*>(stgb + slot);
-              vl[e] = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
-            }
-            if (row0 + rl < p.M) {
-              const uint32_t off = (r_in >> 3) * 1024u + (r_in & 7u) * 128u + (uint32_t)(base_phys + hp * 2) * 16u;
-              ptx::st_global_256(ohi + off, vh[0], vh[1]);
-              ptx::st_global_256(olo + off, vl[0], vl[1]);
-            }
-          }
-          __syncwarp();
-        }
+        if (p.C) epi_store_rows_f32(p.C, p.ldc, row0, nbase, p.M, lane, stg, acc);
+        if (p.O.hi) epi_store_image(p.O, p.o_kb0, mt, nbase, q, row0, p.M, lane, stgb, acc);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -349,6 +472,11 @@ inline int launch_gemm_img(const GemmImgArgs& a, cudaStream_t s, int bn_hint = 0
   if (a.M <= 0) return 0;
   if (a.W.K % 64 || a.W.N % 64 || (a.C && a.ldc % 8) || (a.R && a.ldr % 4))
     return set_error(-1, "gemm_img: K%64, N%64, ldc%8, ldr%4 required");
+  if (a.norm != NORM_NONE) {
+    if (a.W.N != 256 || a.Rimg.hi || a.act != ACT_NONE || (a.nadd && a.ldadd % 4) || (a.norm == NORM_LAYER && (!a.ng || !a.nbeta)))
+      return set_error(-1, "gemm_img: the row-norm epilogue needs N == 256, no activation, fp32 residual");
+    return launch_gemm_img_bn<256>(a, s);
+  }
   if (bn_hint == 64 || a.W.N % 128) return launch_gemm_img_bn<64>(a, s);
   int bn = bn_hint;
   if (!bn) {

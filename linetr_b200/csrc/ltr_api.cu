@@ -261,6 +261,19 @@ static int gemm(const Lin& L, const ActImg& A, int a_kb0, int M, int act, cudaSt
   return launch_gemm_img(a, s, bn_hint);
 }
 
+// GEMM whose epilogue normalises whole rows (N = 256): LayerNorm(acc + bias (+ R)) * g + b (+ add), or
+// the L2 normalisation of the final projection (g == nullptr).  Replaces a GEMM + layernorm256_kernel /
+// final_norm_kernel pair and the fp32 round trip between them.
+static int gemm_norm(const Lin& L, const ActImg& A, int M, cudaStream_t s, int norm, const float* g, const float* beta,
+                     const float* R, int ldr, const float* add, int ldadd, float* C, int ldc, const ActImg* O, int o_kb0) {
+  GemmImgArgs a{};
+  a.A = A; a.W = L.tw; a.bias = L.b; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc;
+  if (O) { a.O = *O; a.o_kb0 = o_kb0; }
+  a.M = M; a.act = ACT_NONE;
+  a.norm = norm; a.eps = 1e-6f; a.ng = g; a.nbeta = beta; a.nadd = add; a.ldadd = ldadd;
+  return launch_gemm_img(a, s, 256);
+}
+
 template <bool TOKEN>
 static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const float* in1, const float* in2, ActImg out,
                             int rows, float width, float height, cudaStream_t s) {
@@ -278,7 +291,7 @@ static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const fl
   return 0;
 }
 
-static int launch_layernorm(const float* in, int ldi, const float* g, const float* b, const float* add, int lda,
+[[maybe_unused]] static int launch_layernorm(const float* in, int ldi, const float* g, const float* b, const float* add, int lda,
                             float* out, int ldo, ActImg oimg, int o_k0, int rows, cudaStream_t s) {
   if (rows <= 0) return 0;
   LaunchScope ls(KC_LAYERNORM, s);
@@ -312,16 +325,15 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   }
   // ---- line stage: V projection (block diagonal over heads), fc + CLS residual, LN, FFN, LN, + line pos ----
   LTR_TRY(gemm(m->wv, w.z, 0, R, ACT_NONE, s, nullptr, 0, &w.ctx, 0, nullptr, 0, nullptr, 0, 64, 4));
-  LTR_TRY(gemm(m->wfc, w.ctx, 0, R, ACT_NONE, s, w.y1pre, 256));
-  LTR_TRY(launch_layernorm(w.y1pre, 256, m->ln1g, m->ln1b, nullptr, 0, w.y1, 256, w.y1i, 0, R, s));
+  // fc (+ CLS residual folded into the bias) -> LayerNorm in the epilogue -> y1 (fp32 rows for the FFN residual + image)
+  LTR_TRY(gemm_norm(m->wfc, w.ctx, R, s, NORM_LAYER, m->ln1g, m->ln1b, nullptr, 0, nullptr, 0, w.y1, 256, &w.y1i, 0));
   LTR_TRY(gemm(m->w1, w.y1i, 0, R, ACT_GELU, s, nullptr, 0, &w.g, 0));
-  LTR_TRY(gemm(m->w2, w.g, 0, R, ACT_NONE, s, w.y2pre, 256, nullptr, 0, w.y1, 256));
   LTR_TRY(launch_small_mlp<false>(m->lpe.head, in.sublines, in.resp, in.angle, w.l128, R, in.image_width,
                                   in.image_height, s));
   LTR_TRY(gemm(m->lpe.l4, w.l128, 0, R, ACT_RELU, s, nullptr, 0, &w.l256, 0));
   LTR_TRY(gemm(m->lpe.l5, w.l256, 0, R, ACT_NONE, s, w.lpos, 256));
-  // sentence = klines_pos + LN(ffn)  -> image xm[:, :256] (the running descriptor)
-  LTR_TRY(launch_layernorm(w.y2pre, 256, m->ln2g, m->ln2b, w.lpos, 256, nullptr, 0, w.xm, 0, R, s));
+  // sentence = klines_pos + LN(y1 + ffn)  -> image xm[:, :256] (the running descriptor), all in the w_2 epilogue
+  LTR_TRY(gemm_norm(m->w2, w.g, R, s, NORM_LAYER, m->ln2g, m->ln2b, w.y1, 256, w.lpos, 256, nullptr, 0, &w.xm, 0));
   // ---- line signature layers ----
   int max_l = in.lines_per_image;
   if (in.cu_lines_host) {
@@ -336,6 +348,10 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
     // x += delta: the running descriptor lives ONLY as the split-bf16 image xm[:, :256] (hi + lo carries
     // ~2^-17 relative precision; an fp32 copy would double the store traffic of this epilogue)
     LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, nullptr, 0, &w.xm, 0, nullptr, 0, &w.xm, 0));
+  }
+  if (!out_cf) {   // rows only: projection + L2 normalisation in one launch
+    LTR_TRY(gemm_norm(m->wf, w.xm, R, s, NORM_L2, nullptr, nullptr, nullptr, 0, nullptr, 0, out_rows, 256, nullptr, 0));
+    return 0;
   }
   LTR_TRY(gemm(m->wf, w.xm, 0, R, ACT_NONE, s, w.yf, 256));
   if (max_l > 0) {
@@ -702,9 +718,11 @@ int ltr_linear(const float* x, int32_t ldx, const float* w, const float* bias, c
   return launch_linear_f32(lin(x, ldx, w, bias, y, ldy, m, n, k, act, res, ldr), as_stream(stream));
 }
 
-int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float* bias, const float* res, int32_t ldr,
-                   float* y, int32_t ldy, float* y_from_image, int32_t m, int32_t n, int32_t k, int32_t act,
-                   int32_t bn_hint, int32_t device, void* stream) {
+struct NormSpec { int norm; float eps; const float* g; const float* beta; const float* add; int ldadd; };
+
+static int linear_img_impl(const float* x, int32_t ldx, const float* w_host, const float* bias, const float* res, int32_t ldr,
+                           float* y, int32_t ldy, float* y_from_image, int32_t m, int32_t n, int32_t k, int32_t act,
+                           int32_t bn_hint, int32_t device, void* stream, const NormSpec& ns) {
   if (!x || !w_host || (!y && !y_from_image)) return set_error(LTR_E_INVALID, "ltr_linear_img: null argument");
   if (n % 64 || k % 64) return set_error(LTR_E_UNSUPPORTED, "ltr_linear_img: n and k must be multiples of 64");
   LTR_CUDA_TRY(cudaSetDevice(device));
@@ -734,6 +752,7 @@ int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float
     a.W.lo = reinterpret_cast<const __nv_bfloat16*>(dw + (size_t)n * k);
     a.W.N = n; a.W.K = k;
     if (y_from_image) { a.O = O; a.o_kb0 = 0; }
+    a.norm = ns.norm; a.eps = ns.eps; a.ng = ns.g; a.nbeta = ns.beta; a.nadd = ns.add; a.ldadd = ns.ldadd;
     rc = launch_gemm_img(a, s, bn_hint);
     if (rc == 0 && y_from_image) {
       LaunchScope ls(KC_LAYERNORM, s);
@@ -745,6 +764,22 @@ int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float
   if (rc != 0) return rc;
   if (ce != cudaSuccess) return set_error(LTR_E_CUDA, std::string("ltr_linear_img: ") + cudaGetErrorString(ce));
   return LTR_OK;
+}
+
+int ltr_linear_img(const float* x, int32_t ldx, const float* w_host, const float* bias, const float* res, int32_t ldr,
+                   float* y, int32_t ldy, float* y_from_image, int32_t m, int32_t n, int32_t k, int32_t act,
+                   int32_t bn_hint, int32_t device, void* stream) {
+  return linear_img_impl(x, ldx, w_host, bias, res, ldr, y, ldy, y_from_image, m, n, k, act, bn_hint, device, stream,
+                         NormSpec{NORM_NONE, 0.f, nullptr, nullptr, nullptr, 0});
+}
+
+int ltr_linear_img_norm(const float* x, int32_t ldx, const float* w_host, const float* bias, const float* res, int32_t ldr,
+                        int32_t norm, float eps, const float* gamma, const float* beta, const float* add, int32_t ldadd,
+                        float* y, int32_t ldy, float* y_from_image, int32_t m, int32_t k, int32_t device, void* stream) {
+  if (norm != NORM_LAYER && norm != NORM_L2) return set_error(LTR_E_INVALID, "ltr_linear_img_norm: norm must be 1 (LayerNorm) or 2 (L2)");
+  if (norm == NORM_LAYER && (!gamma || !beta)) return set_error(LTR_E_INVALID, "ltr_linear_img_norm: LayerNorm needs gamma and beta");
+  return linear_img_impl(x, ldx, w_host, bias, res, ldr, y, ldy, y_from_image, m, 256, k, ACT_NONE, 256, device, stream,
+                         NormSpec{norm, eps, gamma, beta, add, ldadd});
 }
 
 // Micro-benchmark of the image GEMM engine: average device ms per launch of an [m,k]x[n,k]^T

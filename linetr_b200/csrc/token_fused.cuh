@@ -405,28 +405,29 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       }
       worker_sync();
       if (tr) LTR_DBG_STAMP(9);
-      // ---- pooling: thread = channel; z_h[c] = (e0 * cls[c] + sum_n e[n] x[n][c]) / sum
+      // ---- pooling: z_h[c] = (e0 * cls[c] + sum_n e[n] x[n][c]) / sum.  Thread = (4 channels, 2 of the
+      //      4 heads, every second line): one 16-byte x read feeds 8 FMAs (a thread per channel was
+      //      latency-bound at 2 loads per 4 FMAs).  All three indices are warp-uniform except the channels.
       {
-        const int c = wt;
-        const float cv = sCls[c];
-        for (int ln = 0; ln < p.lpt; ++ln) {
+        const int cq = wt & 63, lg = (wt >> 6) & 1, hp = wt >> 7;
+        const float4 cv = *reinterpret_cast<const float4*>(&sCls[cq * 4]);
+        for (int ln = lg; ln < p.lpt; ln += 2) {
           const int gl = line0 + ln;
           if (gl >= p.R) break;
-          const float4 pc = *reinterpret_cast<const float4*>(&sP[1024 + ln * 4]);
-          float z0 = pc.x * cv, z1 = pc.y * cv, z2 = pc.z * cv, z3 = pc.w * cv;
+          const float2 pc = *reinterpret_cast<const float2*>(&sP[1024 + ln * 4 + 2 * hp]);
+          float za0 = pc.x * cv.x, za1 = pc.x * cv.y, za2 = pc.x * cv.z, za3 = pc.x * cv.w;
+          float zb0 = pc.y * cv.x, zb1 = pc.y * cv.y, zb2 = pc.y * cv.z, zb3 = pc.y * cv.w;
           const int rb = ln * p.T;
-#pragma unroll 7
+#pragma unroll 3
           for (int n = 0; n < p.T; ++n) {
-            const float xv = xs[xs_index(rb + n, c)];
-            const float4 pr = *reinterpret_cast<const float4*>(&sP[(rb + n) * 4]);
-            z0 = fmaf(pr.x, xv, z0); z1 = fmaf(pr.y, xv, z1);
-            z2 = fmaf(pr.z, xv, z2); z3 = fmaf(pr.w, xv, z3);
+            const float4 xv = *reinterpret_cast<const float4*>(&xs[xs_index(rb + n, cq * 4)]);
+            const float2 pr = *reinterpret_cast<const float2*>(&sP[(rb + n) * 4 + 2 * hp]);
+            za0 = fmaf(pr.x, xv.x, za0); za1 = fmaf(pr.x, xv.y, za1); za2 = fmaf(pr.x, xv.z, za2); za3 = fmaf(pr.x, xv.w, za3);
+            zb0 = fmaf(pr.y, xv.x, zb0); zb1 = fmaf(pr.y, xv.y, zb1); zb2 = fmaf(pr.y, xv.z, zb2); zb3 = fmaf(pr.y, xv.w, zb3);
           }
-          const float4 iv = *reinterpret_cast<const float4*>(&sInv[ln * 4]);
-          img_store1(p.z, gl, c, z0 * iv.x);
-          img_store1(p.z, gl, 256 + c, z1 * iv.y);
-          img_store1(p.z, gl, 512 + c, z2 * iv.z);
-          img_store1(p.z, gl, 768 + c, z3 * iv.w);
+          const float2 iv = *reinterpret_cast<const float2*>(&sInv[ln * 4 + 2 * hp]);
+          img_store4(p.z, gl, (2 * hp) * 256 + cq * 4, za0 * iv.x, za1 * iv.x, za2 * iv.x, za3 * iv.x);
+          img_store4(p.z, gl, (2 * hp + 1) * 256 + cq * 4, zb0 * iv.y, zb1 * iv.y, zb2 * iv.y, zb3 * iv.y);
         }
       }
       if (tr) LTR_DBG_STAMP(10);

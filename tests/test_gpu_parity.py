@@ -81,6 +81,35 @@ def test_persistent_image_gemm_vs_fp64(M, N_, K, act, bn):
 
 
 # ------------------------------------------------------------------ encoder
+@pytest.mark.parametrize("M,K,norm,with_res,with_add", [(300, 256, 1, False, False), (1000, 1024, 1, True, True),
+                                                         (128 * 150 + 17, 256, 1, True, False), (777, 256, 2, False, False),
+                                                         (128 * 149, 256, 2, False, False)])
+def test_row_norm_epilogue_vs_fp64(M, K, norm, with_res, with_add):
+    """GEMM with the LayerNorm / L2-normalising epilogue (fc+LN1, w_2+LN2+line pos, final_proj+normalize)."""
+    g = torch.Generator().manual_seed(M + K + norm)
+    x = torch.randn(M, K, generator=g) * 0.7 + 0.1
+    w = torch.randn(256, K, generator=g) / K ** 0.5
+    b = torch.randn(256, generator=g) * 0.3
+    res = torch.randn(M, 256, generator=g) if with_res else None
+    add = torch.randn(M, 256, generator=g) if with_add else None
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.2
+    cu = lambda t: t.to(DEV) if t is not None else None
+    y, y2 = _ops.linear_img_norm(cu(x), w, cu(b), cu(res), norm, 1e-6, cu(gamma), cu(beta), cu(add))
+    pre = x.double() @ w.double().T + b.double()
+    if res is not None:
+        pre = pre + res.double()
+    if norm == 1:
+        mu = pre.mean(1, keepdim=True)
+        var = ((pre - mu) ** 2).mean(1, keepdim=True)
+        want = (pre - mu) / torch.sqrt(var + 1e-6) * gamma.double() + beta.double()
+        if add is not None:
+            want = want + add.double()
+    else:
+        want = pre / pre.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    assert (y.cpu().double() - want).abs().max() < 2e-5 * max(1.0, float(want.abs().max()))
+    assert (y2.cpu().double() - want).abs().max() < 4e-5 * max(1.0, float(want.abs().max()))
+
+
 @pytest.mark.parametrize("name", H.ENC_CASES)
 def test_forward_vs_reference_golden_and_oracle(name):
     npz, meta = H.golden()
@@ -286,6 +315,29 @@ def test_host_pipelined_entry_equals_resident():
         torch.cuda.synchronize()
         assert torch.equal(m0, want.matches0) and torch.equal(cnt, want.counts)
         assert np.array_equal(off, want.offsets0)
+
+
+def test_concurrent_streams_share_one_model():
+    """Two groups of pairs encoded + matched on two CUDA streams at the same time through ONE model
+    handle give exactly the serial results (the encode workspace is per stream)."""
+    model, sd = model_for("synthetic:0:1")
+    eng = engine.PairEngine(model, DEV)
+    groups = []
+    for g in range(2):
+        pairs = [syn.make_pair_inputs(700 + 100 * g + p, 128, 21)[:2] for p in range(24)]
+        groups.append(engine.LineBatch.from_images([a for a, _ in pairs] + [b for _, b in pairs]).to(DEV))
+    want = [eng.match_packed(b, 24, 0.8, keep_desc=True) for b in groups]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=DEV) for _ in groups]
+    for _ in range(3):
+        got = []
+        for b, s in zip(groups, streams):
+            with torch.cuda.stream(s):
+                got.append(eng.match_packed(b, 24, 0.8, keep_desc=True))
+        torch.cuda.synchronize()
+        for w, r in zip(want, got):
+            assert torch.equal(w.desc0, r.desc0) and torch.equal(w.desc1, r.desc1)
+            assert torch.equal(w.matches0, r.matches0) and torch.equal(w.counts, r.counts)
 
 
 def test_shipped_checkpoint_cfg1_pair():
