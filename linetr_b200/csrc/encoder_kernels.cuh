@@ -155,50 +155,6 @@ small_mlp_kernel(SmallMlpWeights w, const float* __restrict__ in0, const float* 
 }
 
 // ------------------------------------------------------------------------------------
-// LayerNorm over 256 channels, eps inside the sqrt, biased variance
-// (nn.LayerNorm(d, eps=1e-6), models/line_attention.py:40,83); optional fused add of a
-// second row-major tensor AFTER the normalisation (sentence = klines_pos + enc_out,
-// models/line_transformer.py:128).  One warp per row.
-__global__ void __launch_bounds__(256)
-layernorm256_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, const float* __restrict__ add, int lda,
-                    float* __restrict__ out, int ldo, ActImg oimg, int o_k0, int rows, float eps) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  pdl_launch_dependents();
-  pdl_wait();
-  if (row >= rows) return;
-  const float* p = in + (long long)row * ldi;
-  float4 a = *reinterpret_cast<const float4*>(p + lane * 4);
-  float4 b = *reinterpret_cast<const float4*>(p + 128 + lane * 4);
-  float mean = warp_sum(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w) * (1.f / 256.f);
-  float v[8] = {a.x - mean, a.y - mean, a.z - mean, a.w - mean, b.x - mean, b.y - mean, b.z - mean, b.w - mean};
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
-  float var = warp_sum(ss) * (1.f / 256.f);
-  float inv = 1.f / sqrtf(var + eps);
-  float4 g0 = *reinterpret_cast<const float4*>(gamma + lane * 4), g1 = *reinterpret_cast<const float4*>(gamma + 128 + lane * 4);
-  float4 b0 = *reinterpret_cast<const float4*>(beta + lane * 4), b1 = *reinterpret_cast<const float4*>(beta + 128 + lane * 4);
-  float4 o0 = make_float4(v[0] * inv * g0.x + b0.x, v[1] * inv * g0.y + b0.y, v[2] * inv * g0.z + b0.z, v[3] * inv * g0.w + b0.w);
-  float4 o1 = make_float4(v[4] * inv * g1.x + b1.x, v[5] * inv * g1.y + b1.y, v[6] * inv * g1.z + b1.z, v[7] * inv * g1.w + b1.w);
-  if (add) {
-    const float* q = add + (long long)row * lda;
-    float4 c0 = *reinterpret_cast<const float4*>(q + lane * 4), c1 = *reinterpret_cast<const float4*>(q + 128 + lane * 4);
-    o0.x += c0.x; o0.y += c0.y; o0.z += c0.z; o0.w += c0.w;
-    o1.x += c1.x; o1.y += c1.y; o1.z += c1.z; o1.w += c1.w;
-  }
-  if (out) {
-    float* o = out + (long long)row * ldo;
-    *reinterpret_cast<float4*>(o + lane * 4) = o0;
-    *reinterpret_cast<float4*>(o + 128 + lane * 4) = o1;
-  }
-  if (oimg.hi) {
-    img_store4(oimg, row, o_k0 + lane * 4, o0.x, o0.y, o0.z, o0.w);
-    img_store4(oimg, row, o_k0 + 128 + lane * 4, o1.x, o1.y, o1.z, o1.w);
-  }
-}
-
-// ------------------------------------------------------------------------------------
 // F.normalize(p=2, dim=channel, eps=1e-12) of the final projection
 // (models/line_transformer.py:245-246) and the write of both output layouts:
 // rows [n_lines, 256] and channel-first per image [256, L_i] (the reference's line_desc).

@@ -196,10 +196,11 @@ static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 struct EncodeWs {
   // line stage
   ActImg z, ctx, y1i, g, l128, l256;  // images [R, 1024 / 256 / 256 / 1024 / 128 / 256]
-  float *y1pre, *y1, *y2pre, *lpos;   // fp32 [R, 256]
+  float *y1, *lpos;   // fp32 [R, 256]
   // signature stage
   ActImg xm, hm;       // images [R, 512] = [x | attention output], [R, 512]
-  float *qkv, *yf;       // fp32 [R, 768] (attention gather), [R, 256] (final projection)
+  ActImg qkv;          // image [R, 768]: k-block h = q of head h, 4 + h = k, 8 + h = v
+  float* yf;           // fp32 [R, 256] (final projection when the channel-first layout is requested)
   int64_t bytes;
 };
 
@@ -228,13 +229,11 @@ static EncodeWs carve(const LtrModel* m, int n_lines, int T, char* base) {
   w.g = takei(R, 1024);
   w.l128 = takei(R, 128);
   w.l256 = takei(R, 256);
-  w.y1pre = takef(R * 256);
   w.y1 = takef(R * 256);
-  w.y2pre = takef(R * 256);
   w.lpos = takef(R * 256);
   w.xm = takei(R, 512);
   w.hm = takei(R, 512);
-  w.qkv = takef(R * 768);
+  w.qkv = takei(R, 768);
   w.yf = takef(R * 256);
   w.bytes = off;
   return w;
@@ -291,15 +290,6 @@ static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const fl
   return 0;
 }
 
-[[maybe_unused]] static int launch_layernorm(const float* in, int ldi, const float* g, const float* b, const float* add, int lda,
-                            float* out, int ldo, ActImg oimg, int o_k0, int rows, cudaStream_t s) {
-  if (rows <= 0) return 0;
-  LaunchScope ls(KC_LAYERNORM, s);
-  LTR_CUDA_TRY(launch_pdl(layernorm256_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, s, in, ldi, g, b, add, lda, out, ldo, oimg, o_k0,
-                          rows, 1e-6f));
-  return 0;
-}
-
 #define LTR_TRY(expr)        \
   do {                       \
     int _rc = (expr);        \
@@ -342,7 +332,7 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   }
   for (size_t li = 0; li < m->sig.size(); ++li) {
     const SigLayer& L = m->sig[li];
-    LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, w.qkv, 768));
+    LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, nullptr, 0, &w.qkv, 0));
     LTR_TRY(launch_sig_attention_tc(w.qkv, w.xm, 256, cu, in.lines_per_image, max_l, in.n_images, s));  // o -> xm[:, 256:]
     LTR_TRY(gemm(L.mlp1, w.xm, 0, R, ACT_RELU, s, nullptr, 0, &w.hm, 0));
     // x += delta: the running descriptor lives ONLY as the split-bf16 image xm[:, :256] (hi + lo carries

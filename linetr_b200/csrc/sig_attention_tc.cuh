@@ -4,10 +4,12 @@
 //
 // CTA = (128-query tile, head, image), 256 threads: thread pair <-> query row (TMEM lane), the two
 // threads of a pair own the two halves of the columns.  Per key tile of 128 lines:
-//   * q, k, v fp32 rows are gathered (coalesced, all loads in flight at once) from the qkv buffer,
-//     split into bf16 hi/lo and written as SWIZZLE_128B operand tiles; images are not tile aligned
-//     in the row space, hence the CUDA-core gather instead of TMA.  V is staged exactly like K
-//     ([keys x 64 dims]) and consumed as an MN-major B operand - no transpose anywhere.
+//   * q, k, v arrive as the split-bf16 tile image the qkv GEMM epilogue wrote (k-block h = q of head h,
+//     4 + h = k, 8 + h = v).  Images of the batch are not 128-row aligned in the row space, so the
+//     operand tiles are assembled from 16-byte chunks with cp.async (re-swizzled for the new row
+//     phase, rows past the image zero-filled) - no conversion, no registers, all copies in flight;
+//     v lands behind the S MMA.  V is staged exactly like K ([keys x 64 dims]) and consumed as an
+//     MN-major B operand - no transpose anywhere.
 //   * S = Q K^T      tcgen05 (M128 N128 K64, 3 split products), accumulator in TMEM
 //   * p = exp(s - m), row sums in registers; P written as the A operand of the second MMA
 //     (re-using the Q/K shared memory, which is dead once S is complete)
@@ -31,7 +33,7 @@ struct SigAttnSmem {
   static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
-__global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __restrict__ qkv, ActImg out, int out_k0,
+__global__ void __launch_bounds__(256) sig_attention_tc_kernel(ActImg qkv, ActImg out, int out_k0,
                                                                 const int* __restrict__ cu, int lpi) {
   using S = SigAttnSmem;
   int lb, le;
@@ -79,28 +81,18 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
   pdl_wait();   // qkv of this layer is complete; the previous reader of the output image is done
   if (tid == 0) LTR_DBG_STAMP(31);
 
-  // Coalesced gather of a [128 rows x 64] fp32 tile (rows row0.. of the image, column offset col)
-  // into a bf16 hi/lo operand tile.  float4 f = tid + 256 i  ->  row f/16, floats 4*(f%16)..+3.
-  auto load_tile = [&](float4 (&v)[8], int row0, int col) {
+  // [128 rows x 64] operand tile (hi and lo plane) <- rows row0.. of this image, k-block kb of the qkv image:
+  // chunk f = tid + 256 i -> row f/8, 16-byte chunk f%8 (8 lanes read one 128-byte image line)
+  auto stage_tile = [&](int row0, int kb, uint8_t* hi, uint8_t* lo) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int f = tid + 256 * i, r = f >> 4, c4 = f & 15;
-      v[i] = (row0 + r < L) ? __ldg(reinterpret_cast<const float4*>(qkv + (long long)(lb + row0 + r) * 768 + col + h * 64 + c4 * 4))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto store_tile = [&](const float4 (&v)[8], uint8_t* hi, uint8_t* lo) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int f = tid + 256 * i, r = f >> 4, c4 = f & 15;
-      __nv_bfloat16 hh[4], ll[4];
-      ptx::split_bf16(v[i].x, hh[0], ll[0]);
-      ptx::split_bf16(v[i].y, hh[1], ll[1]);
-      ptx::split_bf16(v[i].z, hh[2], ll[2]);
-      ptx::split_bf16(v[i].w, hh[3], ll[3]);
-      const uint32_t off = ptx::sw128_offset(r, c4 * 4);
-      *reinterpret_cast<uint2*>(hi + off) = make_uint2(ptx::pack_bf16(hh[0], hh[1]), ptx::pack_bf16(hh[2], hh[3]));
-      *reinterpret_cast<uint2*>(lo + off) = make_uint2(ptx::pack_bf16(ll[0], ll[1]), ptx::pack_bf16(ll[2], ll[3]));
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + 256 * i, r = f >> 3, c = f & 7;
+      const bool ok = row0 + r < L;
+      const int gr = lb + row0 + r;
+      const size_t src = ok ? ((size_t)(gr >> 7) * qkv.kblocks + kb) * (IMG_TILE_ELEMS * 2) + ptx::sw128_offset(gr & 127, c * 8) : 0;
+      const uint32_t dst = ptx::sw128_offset(r, c * 8);
+      ptx::cp_async16(hi + dst, reinterpret_cast<const uint8_t*>(qkv.hi) + src, ok ? 16u : 0u);
+      ptx::cp_async16(lo + dst, reinterpret_cast<const uint8_t*>(qkv.lo) + src, ok ? 16u : 0u);
     }
   };
   auto issue_s = [&]() {   // S = Q K^T
@@ -144,11 +136,9 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
     // ---- pass 1: row maxima over all key tiles
     for (int kt = 0; kt < n_kt; ++kt) {
       const int k0 = kt * 128, kn = min(128, L - k0);
-      float4 a[8], b[8];
-      load_tile(a, q0, 0);
-      load_tile(b, k0, 256);
-      store_tile(a, q_hi, q_lo);
-      store_tile(b, k_hi, k_lo);
+      stage_tile(q0, h, q_hi, q_lo);
+      stage_tile(k0, 4 + h, k_hi, k_lo);
+      ptx::cp_async_wait_all();
       ptx::fence_proxy_async_smem();
       __syncthreads();
       if (tid == 0) { ptx::tc_fence_after(); issue_s(); }
@@ -163,16 +153,13 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
   for (int kt = 0; kt < n_kt; ++kt) {
     const int k0 = kt * 128, kn = min(128, L - k0);
     if (tid == 0) LTR_DBG_STAMP(32);
-    {
-      float4 a[8], b[8];
-      load_tile(a, q0, 0);
-      load_tile(b, k0, 256);
-      store_tile(a, q_hi, q_lo);
-      load_tile(a, k0, 512);
-      store_tile(b, k_hi, k_lo);
-      if (tid == 0) LTR_DBG_STAMP(33);
-      store_tile(a, v_hi, v_lo);
-    }
+    stage_tile(q0, h, q_hi, q_lo);
+    stage_tile(k0, 4 + h, k_hi, k_lo);
+    ptx::cp_async_commit();
+    stage_tile(k0, 8 + h, v_hi, v_lo);
+    ptx::cp_async_commit();
+    if (tid == 0) LTR_DBG_STAMP(33);
+    ptx::cp_async_wait_group<1>();   // q and k have landed; v is still in flight behind the S MMA
     if (tid == 0) LTR_DBG_STAMP(34);
     ptx::fence_proxy_async_smem();
     __syncthreads();
@@ -204,6 +191,7 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
             make_uint4(ptx::pack_bf16(ll[0], ll[1]), ptx::pack_bf16(ll[2], ll[3]), ptx::pack_bf16(ll[4], ll[5]), ptx::pack_bf16(ll[6], ll[7]));
       }
     }
+    ptx::cp_async_wait_group<0>();   // v
     ptx::tc_fence_before();
     ptx::fence_proxy_async_smem();
     if (tid == 0) LTR_DBG_STAMP(36);
@@ -252,7 +240,7 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(const float* __re
   if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
 }
 
-inline int launch_sig_attention_tc(const float* qkv, ActImg out, int out_k0, const int* cu, int lpi, int max_l,
+inline int launch_sig_attention_tc(ActImg qkv, ActImg out, int out_k0, const int* cu, int lpi, int max_l,
                                    int n_images, cudaStream_t s) {
   if (max_l <= 0 || n_images <= 0) return 0;
   LTR_CUDA_TRY(ensure_dynamic_smem(sig_attention_tc_kernel, SigAttnSmem::TOTAL));
