@@ -25,25 +25,20 @@ __device__ __forceinline__ void img_store1(const ActImg& a, int row, int k, floa
 }
 // 4 consecutive k (k % 4 == 0): one 8-byte store per plane
 __device__ __forceinline__ void img_store4(const ActImg& a, int row, int k, float v0, float v1, float v2, float v3) {
-  __nv_bfloat16 h[4], l[4];
-  ptx::split_bf16(v0, h[0], l[0]);
-  ptx::split_bf16(v1, h[1], l[1]);
-  ptx::split_bf16(v2, h[2], l[2]);
-  ptx::split_bf16(v3, h[3], l[3]);
+  uint2 h, l;
+  ptx::split2_bf16(v0, v1, h.x, l.x);
+  ptx::split2_bf16(v2, v3, h.y, l.y);
   const size_t i = img_index(a, row, k);
-  *reinterpret_cast<uint2*>(a.hi + i) = make_uint2(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]));
-  *reinterpret_cast<uint2*>(a.lo + i) = make_uint2(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]));
+  *reinterpret_cast<uint2*>(a.hi + i) = h;
+  *reinterpret_cast<uint2*>(a.lo + i) = l;
 }
 // 8 consecutive k (k % 8 == 0): one 16-byte store per plane
 __device__ __forceinline__ void img_store8(const ActImg& a, int row, int k, const float (&v)[8]) {
-  __nv_bfloat16 h[8], l[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) ptx::split_bf16(v[e], h[e], l[e]);
+  uint4 h, l;
+  ptx::split8_bf16(v, h, l);
   const size_t i = img_index(a, row, k);
-  *reinterpret_cast<uint4*>(a.hi + i) =
-      make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
-  *reinterpret_cast<uint4*>(a.lo + i) =
-      make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+  *reinterpret_cast<uint4*>(a.hi + i) = h;
+  *reinterpret_cast<uint4*>(a.lo + i) = l;
 }
 
 }  // namespace ltr

@@ -117,14 +117,11 @@ __device__ __forceinline__ void epi_store_image(const ActImg& O, int kb0, int mt
   // staging: plane [32 rows][4 chunks of 16 B], chunk slot swizzled by (row>>1)&3
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
-    __nv_bfloat16 h[8], l[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) ptx::split_bf16(acc[cc * 8 + e], h[e], l[e]);
+    uint4 h, l;
+    ptx::split8_bf16(&acc[cc * 8], h, l);
     const int slot = (lane * 4 + (cc ^ ((lane >> 1) & 3))) * 16;
-    *reinterpret_cast<uint4*>(stgb + slot) =
-        make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
-    *reinterpret_cast<uint4*>(stgb + 2048 + slot) =
-        make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+    *reinterpret_cast<uint4*>(stgb + slot) = h;
+    *reinterpret_cast<uint4*>(stgb + 2048 + slot) = l;
   }
   __syncwarp();
   const int kb_out = kb0 + (nbase >> 6);
@@ -497,15 +494,12 @@ __global__ void __launch_bounds__(256) to_image_kernel(const float* __restrict__
   const float4 a = *reinterpret_cast<const float4*>(x + (long long)row * ld + k);
   const float4 b = *reinterpret_cast<const float4*>(x + (long long)row * ld + k + 4);
   const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  __nv_bfloat16 h[8], l[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) ptx::split_bf16(v[e], h[e], l[e]);
+  uint4 h, l;
+  ptx::split8_bf16(v, h, l);
   const size_t toff = ((size_t)(row >> 7) * o.kblocks + kb0 + (k >> 6)) * IMG_TILE_ELEMS;
   const uint32_t off = ptx::sw128_offset(row & 127, k & 63);
-  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o.hi + toff) + off) =
-      make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
-  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o.lo + toff) + off) =
-      make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o.hi + toff) + off) = h;
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(o.lo + toff) + off) = l;
 }
 
 // image k-blocks [kb0, kb0 + K/64) -> fp32 rows (hi + lo); test helper.

@@ -180,6 +180,26 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// 2^x with the SFU approximation (2 ulp; results below 2^-126 flush to zero - softmax weights)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Two values at once with the packed conversion (F2FP.BF16.PACK_AB: one instruction per pair and no
+// PRMT packing; the scalar form costs two F2F per value): hi = {bf16(a), bf16(b)} (a in the low
+// half), lo = the same of the residuals.  Bit-identical to split_bf16 + pack_bf16.
+__device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+__device__ __forceinline__ void split8_bf16(const float* v, uint4& hi, uint4& lo) {
+  split2_bf16(v[0], v[1], hi.x, lo.x);
+  split2_bf16(v[2], v[3], hi.y, lo.y);
+  split2_bf16(v[4], v[5], hi.z, lo.z);
+  split2_bf16(v[6], v[7], hi.w, lo.w);
+}
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }

@@ -176,19 +176,16 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(ActImg qkv, ActIm
       ptx::tmem_ld32(t_s + lane_addr + c0, s);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        s[j] = (c0 + j < kn) ? exp2f(fmaf(s[j], LOG2E, -mb)) : 0.f;
+        s[j] = (c0 + j < kn) ? ptx::ex2_approx(fmaf(s[j], LOG2E, -mb)) : 0.f;
         l += s[j];
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        __nv_bfloat16 hh[8], ll[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) ptx::split_bf16(s[j + e], hh[e], ll[e]);
+        uint4 hh, ll;
+        ptx::split8_bf16(&s[j], hh, ll);
         const uint32_t off = half * 16384 + ptx::sw128_offset(row, (c0 & 63) + j);
-        *reinterpret_cast<uint4*>(p_hi + off) =
-            make_uint4(ptx::pack_bf16(hh[0], hh[1]), ptx::pack_bf16(hh[2], hh[3]), ptx::pack_bf16(hh[4], hh[5]), ptx::pack_bf16(hh[6], hh[7]));
-        *reinterpret_cast<uint4*>(p_lo + off) =
-            make_uint4(ptx::pack_bf16(ll[0], ll[1]), ptx::pack_bf16(ll[2], ll[3]), ptx::pack_bf16(ll[4], ll[5]), ptx::pack_bf16(ll[6], ll[7]));
+        *reinterpret_cast<uint4*>(p_hi + off) = hh;
+        *reinterpret_cast<uint4*>(p_lo + off) = ll;
       }
     }
     ptx::cp_async_wait_group<0>();   // v

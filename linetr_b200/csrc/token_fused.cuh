@@ -208,14 +208,11 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
     auto worker_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     // split-bf16 store of 8 consecutive columns into an activation image with nkb k-blocks
     auto act_store8 = [&](int nkb, int col, const float (&v)[8]) {
-      __nv_bfloat16 h[8], l[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) ptx::split_bf16(v[e], h[e], l[e]);
+      uint4 h, l;
+      ptx::split8_bf16(v, h, l);
       const uint32_t off = (col >> 6) * 16384 + ptx::sw128_offset(r_in, col & 63);
-      *reinterpret_cast<uint4*>(act + off) =
-          make_uint4(ptx::pack_bf16(h[0], h[1]), ptx::pack_bf16(h[2], h[3]), ptx::pack_bf16(h[4], h[5]), ptx::pack_bf16(h[6], h[7]));
-      *reinterpret_cast<uint4*>(act + nkb * 16384 + off) =
-          make_uint4(ptx::pack_bf16(l[0], l[1]), ptx::pack_bf16(l[2], l[3]), ptx::pack_bf16(l[4], l[5]), ptx::pack_bf16(l[6], l[7]));
+      *reinterpret_cast<uint4*>(act + off) = h;
+      *reinterpret_cast<uint4*>(act + nkb * 16384 + off) = l;
     };
     // P0: narrow MLP 3 -> 32 -> 64 (+ReLU) for this thread's token row of tile `t`; the thread produces
     // outputs [32*half, 32*half+32) and keeps them as packed split-bf16 registers until p0_store().
@@ -248,11 +245,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
           }
           o[j] = fmaxf(a, 0.f);
         }
-        __nv_bfloat16 h0, l0, h1b, l1b;
-        ptx::split_bf16(o[0], h0, l0);
-        ptx::split_bf16(o[1], h1b, l1b);
-        p0_hi[n0 >> 1] = ptx::pack_bf16(h0, h1b);
-        p0_lo[n0 >> 1] = ptx::pack_bf16(l0, l1b);
+        ptx::split2_bf16(o[0], o[1], p0_hi[n0 >> 1], p0_lo[n0 >> 1]);
       }
     };
     auto p0_store = [&]() {
