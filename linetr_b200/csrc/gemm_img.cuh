@@ -67,6 +67,24 @@ struct GemmImgCfg {
 };
 
 
+// GELU(x) = x * Phi(x) with the erf form the reference uses (F.gelu default, models/line_attention.py:92).
+// erfc(u) = P(t) exp(-u^2), t = 1 / (1 + 0.3275911 u)  (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 - the
+// size of an fp32 rounding of erf itself) costs 2 SFU ops + ~12 FMAs; erff() is ~35 instructions per value
+// and made the 256 -> 1024 FFN epilogue twice as long as its main loop.  Written with erfc on both
+// sides of zero so that the negative tail has no 1 - erf cancellation.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.f)));
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  pl *= t;
+  const float g = 0.5f * x * pl * ptx::ex2_approx(u * u * -1.4426950408889634f);   // 0.5 x erfc(|x| / sqrt 2)
+  return x < 0.f ? g : x - g;
+}
+
 // ---------------------------------------------------------------- epilogue building blocks
 // One epilogue warp owns 32 accumulator rows (row0 .. row0+31, lane = row) and works on 32-column
 // chunks `acc[32]` starting at global column `nbase`.  Global traffic goes through the warp's 4 KB
@@ -388,7 +406,7 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
           for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
         } else if (p.act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = 0.5f * acc[j] * (1.f + erff(acc[j] * 0.70710678118654752440f));
+          for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
         }
         if (p.R) epi_add_rows_f32(p.R, p.ldr, row0, nbase, p.M, lane, stg, acc);
         if (p.Rimg.hi) {

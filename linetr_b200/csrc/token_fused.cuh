@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
   uint64_t* a_ready = bars + 4;     // workers -> MMA: A operand image complete (256 arrivals)
   uint64_t* acc_ready = bars + 5;   // MMA -> workers: accumulator complete (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* dbar = bars + 8;        // [4] descriptor columns {32 s .. 32 s + 32} u {128 + 32 s ..} of the tile have landed
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     ptx::mbar_init(a_ready, 256);
     ptx::mbar_init(acc_ready, 1);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&dbar[i], 256);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
     const int r_in = q * 32 + lane;    // token row inside the tile
     const int wt = tid - 64;           // 0..255
     const int rows_used = p.lpt * p.T;
-    uint32_t nacc = 0;
+    uint32_t nacc = 0, dph = 0;   // phase parities: accumulator barrier, descriptor-group barriers
     auto worker_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     // split-bf16 store of 8 consecutive columns into an activation image with nkb k-blocks
     auto act_store8 = [&](int nkb, int col, const float (&v)[8]) {
@@ -315,24 +317,30 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       ptx::tc_fence_after();
       if (tr) LTR_DBG_STAMP(6);
       float* xs = reinterpret_cast<float*>(act);
-      {   // phase A: the tile's descriptors are ONE contiguous 128 KB range: coalesced copy into the
-          // (now dead) activation region, in the swizzled x layout
+      {   // phase A: the tile's descriptors are ONE contiguous 128 KB range: coalesced cp.async copy into the
+          // (now dead) activation region, in the swizzled x layout.  Issued as four 32 KB groups in the
+          // order the epilogue consumes them (group s = columns 32 s.. of both column halves); every
+          // group reports to its own mbarrier, so chunk s is processed while groups s+1.. are in flight.
         const float4* dsrc = reinterpret_cast<const float4*>(p.desc + tok0 * 256);
         const long long rows_avail = n_tok_total - tok0;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {   // 32 x 16 B per thread, all in flight (cp.async, no registers)
-          const int f = wt + 256 * i, r = f >> 6, c4 = f & 63;
-          const bool ok = r < rows_used && r < rows_avail;
-          ptx::cp_async16(&xs[xs_index(r, c4 * 4)], ok ? (const void*)(dsrc + f) : (const void*)p.desc, ok ? 16u : 0u);
+#pragma unroll 1
+        for (int sgrp = 0; sgrp < 4; ++sgrp) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {   // 8 x 16 B per thread and group (no registers)
+            const int g = wt + 256 * i, r = g >> 4, j = g & 15;
+            const int c4 = (j >> 3) * 32 + sgrp * 8 + (j & 7);   // float4 index inside the row
+            const bool ok = r < rows_used && r < rows_avail;
+            ptx::cp_async16(&xs[xs_index(r, c4 * 4)], ok ? (const void*)(dsrc + r * 64 + c4) : (const void*)p.desc, ok ? 16u : 0u);
+          }
+          ptx::cp_async_mbar_arrive_noinc(&dbar[sgrp]);
         }
-        ptx::cp_async_wait_all();
       }
-      worker_sync();
       float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         float acc[32];
         ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+        ptx::mbar_wait(&dbar[(c0 >> 5) & 3], dph);   // this column group of every row has landed
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const int n = c0 + j;
@@ -354,6 +362,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
           sc3 = fmaf(x.x, u3.x, fmaf(x.y, u3.y, fmaf(x.z, u3.z, fmaf(x.w, u3.w, sc3))));
         }
       }
+      dph ^= 1;
       ptx::tc_fence_before();
       *reinterpret_cast<float4*>(&sSc[(half * 128 + r_in) * 4]) = make_float4(sc0, sc1, sc2, sc3);
       if (tr) LTR_DBG_STAMP(7);
