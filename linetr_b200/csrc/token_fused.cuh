@@ -18,6 +18,7 @@
 // 256 worker threads (thread pair per token row: lane = row within the warp's TMEM lane
 // quarter, `half` = which half of the output columns).
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "act_img.cuh"
 #include "common.cuh"
 #include "tc_weight.cuh"
@@ -61,12 +62,14 @@ struct TokenFusedSmem {
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;       // + alignment slack
 };
 
-// x tile in the activation region: fp32 [128 rows][256], 16-byte chunks XOR-swizzled by row & 7
+// x tile in the activation region: 8 column blocks of [128 rows x 32 fp32 (128 B)], each row's eight
+// 16-byte chunks XOR-swizzled by row & 7 - the layout a SWIZZLE_128B tensor-map box load produces.
+// Conflict-free both for a thread per row (L5 epilogue) and for a thread per channel quad (pooling).
 __device__ __forceinline__ int xs_index(int row, int col) {
-  return row * 256 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
+  return (col >> 5) * 4096 + row * 32 + (((((col >> 2) & 7) ^ (row & 7)) << 2) | (col & 3));
 }
 
-__global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
+__global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, const __grid_constant__ CUtensorMap desc_map) {
   using S = TokenFusedSmem;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -105,7 +108,8 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     ptx::mbar_init(a_ready, 256);
     ptx::mbar_init(acc_ready, 1);
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(&dbar[i], 256);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&dbar[i], 1);
+    ptx::prefetch_tensormap(&desc_map);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -261,7 +265,6 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int line0 = tile * p.lpt;
       const long long tok0 = (long long)line0 * p.T;
-      const long long n_tok_total = (long long)p.R * p.T;
       const bool tr = (tile == blockIdx.x + gridDim.x) && warp == 2 && lane == 0;   // trace the CTA's 2nd tile
       if (tr) LTR_DBG_STAMP(0);
       // ---- P0 result of THIS tile (computed during the previous tile's L5 MMAs) -> h64 operand tile
@@ -317,30 +320,27 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
       ptx::tc_fence_after();
       if (tr) LTR_DBG_STAMP(6);
       float* xs = reinterpret_cast<float*>(act);
-      {   // phase A: the tile's descriptors are ONE contiguous 128 KB range: coalesced cp.async copy into the
-          // (now dead) activation region, in the swizzled x layout.  Issued as four 32 KB groups in the
-          // order the epilogue consumes them (group s = columns 32 s.. of both column halves); every
-          // group reports to its own mbarrier, so chunk s is processed while groups s+1.. are in flight.
-        const float4* dsrc = reinterpret_cast<const float4*>(p.desc + tok0 * 256);
-        const long long rows_avail = n_tok_total - tok0;
-#pragma unroll 1
-        for (int sgrp = 0; sgrp < 4; ++sgrp) {
+      // phase A: the tile's descriptors ([128 token rows x 256] fp32, the one mandatory HBM stream of this
+      // stage, prefetched into L2 a tile ahead) -> the (now dead) activation region by TMA: eight
+      // SWIZZLE_128B boxes of 32 columns, issued as four groups in the order the epilogue consumes
+      // them (group s = column blocks s and 4 + s), one mbarrier per group.  Rows past the end of the
+      // batch are zero-filled by the TMA unit; rows of the next tile that ride along are never used.
+      if (wt == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {   // 8 x 16 B per thread and group (no registers)
-            const int g = wt + 256 * i, r = g >> 4, j = g & 15;
-            const int c4 = (j >> 3) * 32 + sgrp * 8 + (j & 7);   // float4 index inside the row
-            const bool ok = r < rows_used && r < rows_avail;
-            ptx::cp_async16(&xs[xs_index(r, c4 * 4)], ok ? (const void*)(dsrc + r * 64 + c4) : (const void*)p.desc, ok ? 16u : 0u);
-          }
-          ptx::cp_async_mbar_arrive_noinc(&dbar[sgrp]);
+        for (int sgrp = 0; sgrp < 4; ++sgrp) {
+          ptx::mbar_arrive_expect_tx(&dbar[sgrp], 2 * 16384);
+          ptx::tma_load_2d(xs + sgrp * 4096, &desc_map, sgrp * 32, (int)tok0, &dbar[sgrp]);
+          ptx::tma_load_2d(xs + (4 + sgrp) * 4096, &desc_map, (4 + sgrp) * 32, (int)tok0, &dbar[sgrp]);
         }
       }
+      if (tr) LTR_DBG_STAMP(12);
       float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
 #pragma unroll 1
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         float acc[32];
         ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
         ptx::mbar_wait(&dbar[(c0 >> 5) & 3], dph);   // this column group of every row has landed
+        if (tr) LTR_DBG_STAMP(13 + ((c0 >> 5) & 3));
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const int n = c0 + j;
@@ -442,19 +442,49 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p) {
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TensorMapEncodeTiledFn tensor_map_encoder() {
+  static TensorMapEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 inline int launch_token_fused(TokenFusedArgs a, cudaStream_t s) {
   if (a.R <= 0) return 0;
   if (a.T < 1 || a.T > 128) return set_error(-1, "token_fused: T must be in 1..128");
+  if ((long long)a.R * a.T >= (1ll << 31)) return set_error(-1, "token_fused: more than 2^31 tokens in one call");
+  if (reinterpret_cast<uintptr_t>(a.desc) % 16) return set_error(-1, "token_fused: desc_sublines must be 16-byte aligned");
   LTR_CUDA_TRY(ensure_dynamic_smem(token_fused_kernel, TokenFusedSmem::TOTAL));
   a.lpt = 128 / a.T;
   a.n_tiles = cdiv(a.R, a.lpt);
+  // tensor map of the sampled descriptors viewed as [R*T rows, 256] fp32; box = 32 columns (128 B) x 128 rows
+  TensorMapEncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return set_error(-1, "token_fused: cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap map;
+  const cuuint64_t gdim[2] = {256, (cuuint64_t)a.R * a.T};
+  const cuuint64_t gstride[1] = {256 * sizeof(float)};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.desc), gdim, gstride, box, estride,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return set_error(-1, "token_fused: cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
   LaunchScope ls(KC_TOKEN_FUSED, s);
-  LTR_CUDA_TRY(launch_pdl(token_fused_kernel, dim3(grid), dim3(320), TokenFusedSmem::TOTAL, s, a));
+  LTR_CUDA_TRY(launch_pdl(token_fused_kernel, dim3(grid), dim3(320), TokenFusedSmem::TOTAL, s, a, map));
   return 0;
 }
 
