@@ -139,17 +139,6 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
         ++it;
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        {   // pull the NEXT tile's descriptors (the mandatory HBM read of this stage) into L2:
-            // one prefetch per 128-byte line, spread over the 32 lanes of this warp
-          const long long nt = (long long)(tile + gridDim.x) * p.lpt * p.T;
-          const long long total = (long long)p.R * p.T;
-          if (nt < total) {
-            const long long rows = min((long long)p.lpt * p.T, total - nt);
-            const char* base = reinterpret_cast<const char*>(p.desc + nt * 256);
-            for (long long ln = lane; ln < rows * 8; ln += 32)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ln * 128));
-          }
-        }
         push(p.W3, 0, 0);
         for (int nb = 0; nb < 2; ++nb)
           for (int kb = 0; kb < 2; ++kb) push(p.W4, nb, kb);
@@ -321,7 +310,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       if (tr) LTR_DBG_STAMP(6);
       float* xs = reinterpret_cast<float*>(act);
       // phase A: the tile's descriptors ([128 token rows x 256] fp32, the one mandatory HBM stream of this
-      // stage, prefetched into L2 a tile ahead) -> the (now dead) activation region by TMA: eight
+      // stage) -> the (now dead) activation region by TMA: eight
       // SWIZZLE_128B boxes of 32 columns, issued as four groups in the order the epilogue consumes
       // them (group s = column blocks s and 4 + s), one mbarrier per group.  Rows past the end of the
       // batch are zero-filled by the TMA unit; rows of the next tile that ride along are never used.
