@@ -83,6 +83,8 @@ class ModelHandle:
         key = torch.cuda.current_stream(dev).cuda_stream
         ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
+            if len(self._ws) >= 16:   # callers that keep creating streams: do not hoard one workspace per dead stream
+                self._ws.clear()
             ws = self._ws[key] = torch.empty(need, dtype=torch.uint8, device=dev)
         return ws
 
