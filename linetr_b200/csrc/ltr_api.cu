@@ -261,8 +261,8 @@ static int gemm(const Lin& L, const ActImg& A, int a_kb0, int M, int act, cudaSt
 }
 
 // GEMM whose epilogue normalises whole rows (N = 256): LayerNorm(acc + bias (+ R)) * g + b (+ add), or
-// the L2 normalisation of the final projection (g == nullptr).  Replaces a GEMM + layernorm256_kernel /
-// final_norm_kernel pair and the fp32 round trip between them.
+// the L2 normalisation of the final projection (g == nullptr): one launch instead of a GEMM, a
+// normalisation kernel and the fp32 round trip between them.
 static int gemm_norm(const Lin& L, const ActImg& A, int M, cudaStream_t s, int norm, const float* g, const float* beta,
                      const float* R, int ldr, const float* add, int ldadd, float* C, int ldc, const ActImg* O, int o_kb0) {
   GemmImgArgs a{};

@@ -11,8 +11,9 @@
 // Replaces WordPositionalEncoder (models/line_transformer.py:61-73), `desc + pos` and the CLS
 // concat (:117-121) and the attention part of MultiHeadAttention restricted to the CLS query row
 // (models/line_attention.py:13-21,55-63), i.e. what a narrow-MLP kernel, two GEMM launches and a
-// pooling kernel would do through global memory.  Only `desc` (the mandatory HBM read), the
-// weights (L2 resident, streamed by TMA through a 2-slot ring) and the pooled z leave/enter the SM.
+// pooling kernel would do through global memory.  Only `desc` (the mandatory HBM read, one
+// SWIZZLE_128B tensor-map TMA per 32-column block of the tile), the weights (L2 resident, streamed
+// by 1-D TMA through a 2-slot ring) and the pooled z leave/enter the SM.
 //
 // Warp roles: warp 0 = TMA weight producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-9 =
 // 256 worker threads (thread pair per token row: lane = row within the warp's TMEM lane
