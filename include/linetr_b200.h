@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define LTR_ABI_VERSION 1
+#define LTR_ABI_VERSION 2
 
 #define LTR_OK 0
 #define LTR_E_INVALID (-1)   /* bad argument / missing checkpoint tensor / shape mismatch */
@@ -94,11 +94,25 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
                int32_t device, LtrModel** out);
 void ltr_destroy(LtrModel* m);
 
-/* desc_cf_out: unit-norm descriptors channel-first, image i at offset d_model*cu_lines[i],
- *              element (c, l) at c*L_i + l - for a uniform batch exactly the reference's
- *              line_desc [B, d_model, L].  May be NULL.
- * desc_rows_out: the same descriptors row-major [n_lines, d_model] (matcher layout). May be NULL. */
-int ltr_encode(LtrModel* m, const LtrEncodeInput* in, float* desc_cf_out, float* desc_rows_out,
+/* Outputs of ltr_encode (device, caller-owned; any of them may be NULL).
+ * desc_cf:    unit-norm descriptors channel-first, image i at offset d_model*cu_lines[i],
+ *             element (c, l) at c*L_i + l - for a uniform batch exactly the reference's
+ *             line_desc [B, d_model, L].
+ * desc_rows:  the same descriptors row-major [n_lines, d_model] (matcher layout).
+ * desc_tiles: the same descriptors as the split-bf16 "tile image" the tensor-core matcher
+ *             contracts (ltr_desc_tiles_bytes(n_lines) bytes, opaque): hand it to ltr_match
+ *             (LtrMatchInput.tiles0/1) and the matcher skips its own fp32 -> tile conversion.
+ *             Needs desc_rows != NULL and desc_cf == NULL (it is written by the same fused
+ *             projection + L2-normalisation launch as desc_rows). */
+typedef struct {
+  float* desc_cf;
+  float* desc_rows;
+  void* desc_tiles;
+} LtrEncodeOutput;
+
+int64_t ltr_desc_tiles_bytes(int32_t n_lines);
+
+int ltr_encode(LtrModel* m, const LtrEncodeInput* in, const LtrEncodeOutput* out,
                void* workspace, int64_t workspace_bytes, void* stream);
 
 #define LTR_LAYOUT_ROWS 0          /* [n, d] */
@@ -131,6 +145,19 @@ typedef struct {
                                0 = max_k0*max_k1 (or max_n0*max_n1 without merging) */
   float nn_thresh;         /* strict '<' (models/nn_matcher.py:18) */
   int32_t mutual;
+  int32_t total_n0, total_n1; /* total sublines per side (required with cu0/cu1; 0 = n_pairs*n0/n1) */
+  int32_t dist_mode;       /* 0: 2 - 2<a,b> (unit descriptors; models/nn_matcher.py:37-38,
+                              models/line_process.py:199-200); 1: |a|^2 + |b|^2 - 2<a,b>
+                              (evaluations/matcher.py:66-70); mode 1 needs d == 256, no merging */
+  /* Optional: descriptor tile images written by ltr_encode (LtrEncodeOutput.desc_tiles) for the SAME
+   * descriptors as desc0/desc1.  Usable when d == 256, the batch is uniform (cu0 == cu1 == NULL),
+   * n0 % 128 == 0, n1 % 128 == 0 and tiles_row0_s % 128 == 0; tiles_lines_s = the n_lines the image
+   * was produced for, tiles_row0_s = row of this side's first line inside it (both sides may live in
+   * one image: one ltr_encode over 2P images).  NULL = the matcher converts desc0/desc1 itself. */
+  const void* tiles0;
+  const void* tiles1;
+  int32_t tiles_lines0, tiles_lines1;
+  int32_t tiles_row0_0, tiles_row0_1;
 } LtrMatchInput;
 
 /* Outputs (device).  Keyline k of side 0 lives at index cuk0[p]+k (cu0[p]+k without
@@ -141,7 +168,12 @@ typedef struct {
  * counts[p]   = number of matches of pair p;
  * dist_key    = keyline distance matrices, pair p at p*dist_pair_stride, row-major
  *               [K0_p, K1_p] (Matching's 'matching_scores_l');
- * dist_sub    = scratch for subline distances [n_pairs, max_n0*max_n1], merging only. */
+ * dist_sub    = scratch for subline distances [n_pairs, max_n0*max_n1], merging only.
+ * workspace   = device scratch of ltr_match_workspace_bytes(in) bytes (tile images, per-line
+ *               argmin slots).
+ * dist_key may be NULL when there is no key-line merging and d == 256: the distance matrix is
+ * then never materialised (row argmin lives in the epilogue of the tensor-core contraction).
+ * matches0 == NULL (with scores0, nn1, counts) computes dist_key only (get_dist_matrix). */
 typedef struct {
   int32_t* matches0;
   float* scores0;
@@ -149,7 +181,11 @@ typedef struct {
   int32_t* counts;
   float* dist_key;
   float* dist_sub;
+  void* workspace;
+  int64_t workspace_bytes;
 } LtrMatchOutput;
+
+int64_t ltr_match_workspace_bytes(const LtrMatchInput* in);
 
 int ltr_match(const LtrMatchInput* in, const LtrMatchOutput* out, int32_t device, void* stream);
 
@@ -225,21 +261,6 @@ int ltr_linear_img_norm(const float* x, int32_t ldx, const float* w_host, const 
                         const float* res, int32_t ldr, int32_t norm, float eps, const float* gamma,
                         const float* beta, const float* add, int32_t ldadd, float* y, int32_t ldy,
                         float* y_from_image, int32_t m, int32_t k, int32_t device, void* stream);
-
-/* Micro-benchmark of the image-operand GEMM engine (zero-filled operands, timing only):
- * average device milliseconds per launch.  out_mode: 0 fp32 rows, 1 image, 2 both. */
-float ltr_gemm_bench(int32_t m, int32_t n, int32_t k, int32_t bn_hint, int32_t out_mode, int32_t iters,
-                     int32_t device);
-
-/* clock64 stamps of CTA 0 recorded by the last ltr_gemm_bench call (64 slots, 16 per tile:
- * 0 MMA acc_empty ok, 1 first operands landed, 2 MMAs issued, 3 epilogue acc_full ok, 4 first
- * TMEM chunk read, 5 epilogue done, 6 producer slot free).  Debug aid. */
-const unsigned long long* ltr_gemm_trace(void);
-
-/* Debug tracing: kernels instrumented with LTR_DBG_STAMP store clock64 stamps of their first
- * CTA into a 128-slot device array while tracing is armed. */
-void ltr_debug_trace_arm(int32_t on);
-int ltr_debug_trace_read(unsigned long long* out128);
 
 /* Instrumentation.  Kernel launches issued by this library since the last reset. */
 int64_t ltr_launch_count(void);

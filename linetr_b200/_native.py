@@ -21,9 +21,13 @@ LAYOUT_CHANNEL_FIRST = 1
 # Every symbol include/linetr_b200.h declares (tests check the library exports all of them).
 EXPORTED_SYMBOLS = (
     "ltr_abi_version", "ltr_last_error", "ltr_create", "ltr_destroy", "ltr_encode_workspace_bytes",
-    "ltr_encode", "ltr_match", "ltr_match_distmat", "ltr_merge_sublines", "ltr_tokenize", "ltr_linear", "ltr_linear_img", "ltr_linear_img_norm", "ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read", "ltr_launch_count",
-    "ltr_reset_launch_count", "ltr_profile_begin", "ltr_profile_end",
+    "ltr_desc_tiles_bytes", "ltr_encode", "ltr_match_workspace_bytes", "ltr_match", "ltr_match_distmat",
+    "ltr_merge_sublines", "ltr_tokenize", "ltr_linear", "ltr_linear_img", "ltr_linear_img_norm",
+    "ltr_launch_count", "ltr_reset_launch_count", "ltr_profile_begin", "ltr_profile_end",
 )
+# include/linetr_b200_debug.h (micro-benchmark / tracing hooks; not part of the drop-in boundary)
+DEBUG_SYMBOLS = ("ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read")
+ABI_VERSION = 2
 
 
 class LtrError(RuntimeError):
@@ -47,18 +51,26 @@ class LtrEncodeInput(C.Structure):
                 ("lines_per_image", C.c_int32), ("image_width", C.c_float), ("image_height", C.c_float)]
 
 
+class LtrEncodeOutput(C.Structure):
+    _fields_ = [("desc_cf", C.c_void_p), ("desc_rows", C.c_void_p), ("desc_tiles", C.c_void_p)]
+
+
 class LtrMatchInput(C.Structure):
     _fields_ = [("desc0", C.c_void_p), ("desc1", C.c_void_p), ("layout", C.c_int32), ("d", C.c_int32),
                 ("n_pairs", C.c_int32), ("n0", C.c_int32), ("n1", C.c_int32),
                 ("cu0", C.c_void_p), ("cu1", C.c_void_p), ("sub_off0", C.c_void_p), ("sub_off1", C.c_void_p),
                 ("cuk0", C.c_void_p), ("cuk1", C.c_void_p),
                 ("max_n0", C.c_int32), ("max_n1", C.c_int32), ("max_k0", C.c_int32), ("max_k1", C.c_int32),
-                ("dist_pair_stride", C.c_int64), ("nn_thresh", C.c_float), ("mutual", C.c_int32)]
+                ("dist_pair_stride", C.c_int64), ("nn_thresh", C.c_float), ("mutual", C.c_int32),
+                ("total_n0", C.c_int32), ("total_n1", C.c_int32), ("dist_mode", C.c_int32),
+                ("tiles0", C.c_void_p), ("tiles1", C.c_void_p), ("tiles_lines0", C.c_int32), ("tiles_lines1", C.c_int32),
+                ("tiles_row0_0", C.c_int32), ("tiles_row0_1", C.c_int32)]
 
 
 class LtrMatchOutput(C.Structure):
     _fields_ = [("matches0", C.c_void_p), ("scores0", C.c_void_p), ("nn1", C.c_void_p),
-                ("counts", C.c_void_p), ("dist_key", C.c_void_p), ("dist_sub", C.c_void_p)]
+                ("counts", C.c_void_p), ("dist_key", C.c_void_p), ("dist_sub", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 class LtrTokenizeInput(C.Structure):
@@ -93,9 +105,13 @@ def load():
     lib.ltr_destroy.restype = None
     lib.ltr_encode_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.ltr_encode_workspace_bytes.restype = C.c_int64
-    lib.ltr_encode.argtypes = [C.c_void_p, C.POINTER(LtrEncodeInput), C.c_void_p, C.c_void_p, C.c_void_p,
+    lib.ltr_desc_tiles_bytes.argtypes = [C.c_int32]
+    lib.ltr_desc_tiles_bytes.restype = C.c_int64
+    lib.ltr_encode.argtypes = [C.c_void_p, C.POINTER(LtrEncodeInput), C.POINTER(LtrEncodeOutput), C.c_void_p,
                                C.c_int64, C.c_void_p]
     lib.ltr_encode.restype = C.c_int
+    lib.ltr_match_workspace_bytes.argtypes = [C.POINTER(LtrMatchInput)]
+    lib.ltr_match_workspace_bytes.restype = C.c_int64
     lib.ltr_match.argtypes = [C.POINTER(LtrMatchInput), C.POINTER(LtrMatchOutput), C.c_int32, C.c_void_p]
     lib.ltr_match.restype = C.c_int
     lib.ltr_match_distmat.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_float,
@@ -131,7 +147,7 @@ def load():
     lib.ltr_profile_begin.restype = None
     lib.ltr_profile_end.argtypes = [C.POINTER(C.c_char_p), c_float_p, c_int32_p, C.c_int32]
     lib.ltr_profile_end.restype = C.c_int
-    if lib.ltr_abi_version() != 1:
+    if lib.ltr_abi_version() != ABI_VERSION:
         raise LtrError("linetr_b200: ABI version mismatch between _native.py and the shared library")
     _lib = lib
     return lib

@@ -90,12 +90,13 @@ class ModelHandle:
 
 
 def encode(handle: ModelHandle, sublines, resp, angle, pnt, desc, score, image_wh, *, lines_per_image=None,
-           cu_lines_host=None, cu_lines_dev=None, want_cf=True, want_rows=False):
+           cu_lines_host=None, cu_lines_dev=None, want_cf=True, want_rows=False, want_tiles=False):
     """ltr_encode on flattened lines.
 
     sublines [R,2,2], resp [R,1], angle [R,2], pnt [R,T,2], desc [R,T,256], score [R,T,1]; either
     `lines_per_image` (uniform batch) or `cu_lines_host` (np.int32 [B+1]) + `cu_lines_dev`.
-    Returns (desc_cf flat [256*R] or None, desc_rows [R,256] or None).
+    Returns (desc_cf flat [256*R] or None, desc_rows [R,256] or None), plus the descriptor tile image
+    (uint8 tensor, the matcher's operand format) as a third element when `want_tiles`.
     """
     for nm, t in (("sublines", sublines), ("resp_sublines", resp), ("angle_sublines", angle),
                   ("pnt_sublines", pnt), ("desc_sublines", desc), ("score_sublines", score)):
@@ -117,25 +118,51 @@ def encode(handle: ModelHandle, sublines, resp, angle, pnt, desc, score, image_w
         n_images = R // lpi if lpi > 0 else 0
     out_cf = torch.empty(R * 256, dtype=torch.float32, device=dev) if want_cf else None
     out_rows = torch.empty((R, 256), dtype=torch.float32, device=dev) if want_rows else None
+    out_tiles = None
+    if want_tiles:
+        if want_cf or not want_rows:
+            raise N.LtrError("encode: want_tiles needs want_rows=True and want_cf=False")
+        out_tiles = torch.empty(max(int(handle._lib.ltr_desc_tiles_bytes(R)), 1), dtype=torch.uint8, device=dev)
     if R == 0 or n_images == 0:
-        return out_cf, out_rows
+        return (out_cf, out_rows, out_tiles) if want_tiles else (out_cf, out_rows)
     ws = handle.workspace(n_images, R, T)
     inp = N.LtrEncodeInput(
         sublines.data_ptr(), resp.data_ptr(), angle.data_ptr(), pnt.data_ptr(), desc.data_ptr(), score.data_ptr(),
         cu_lines_host.ctypes.data if cu_lines_host is not None else None,
         cu_lines_dev.data_ptr() if cu_lines_host is not None else None,
         n_images, R, T, lpi, float(image_wh[0]), float(image_wh[1]))
+    outp = N.LtrEncodeOutput(out_cf.data_ptr() if out_cf is not None else None,
+                             out_rows.data_ptr() if out_rows is not None else None,
+                             out_tiles.data_ptr() if out_tiles is not None else None)
     with torch.cuda.device(dev):
-        rc = handle._lib.ltr_encode(handle.ptr, C.byref(inp), _ptr(out_cf), _ptr(out_rows), _ptr(ws),
-                                    ws.numel(), _stream_ptr(dev))
+        rc = handle._lib.ltr_encode(handle.ptr, C.byref(inp), C.byref(outp), _ptr(ws), ws.numel(), _stream_ptr(dev))
     N.check(rc, "ltr_encode")
-    return out_cf, out_rows
+    return (out_cf, out_rows, out_tiles) if want_tiles else (out_cf, out_rows)
+
+
+_match_ws = {}   # (device index, stream) -> uint8 scratch tensor, grown on demand
+
+
+def _match_workspace(dev, need: int) -> torch.Tensor:
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _match_ws.get(key)
+    if ws is None or ws.numel() < need:
+        if len(_match_ws) >= 16:
+            _match_ws.clear()
+        ws = _match_ws[key] = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    return ws
 
 
 def match_descriptors(desc0, desc1, layout, n_pairs, nn_thresh, mutual=True, *, n0=0, n1=0, cu0=None, cu1=None,
                       max_n0=0, max_n1=0, sub_off0=None, sub_off1=None, cuk0=None, cuk1=None, max_k0=0, max_k1=0,
-                      total_k0=None, total_k1=None, d=256):
-    """ltr_match.  Returns dict(matches0, scores0, nn1, counts, dist_key, stride)."""
+                      total_k0=None, total_k1=None, d=256, want_dist=True, want_matches=True, dist_mode=0,
+                      tiles0=None, tiles1=None, tiles_lines=(0, 0), tiles_row0=(0, 0)):
+    """ltr_match.  Returns dict(matches0, scores0, nn1, counts, dist_key, stride).
+
+    want_dist=False (no key-line merging, d == 256) never materialises the distance matrix: the row
+    argmin lives in the epilogue of the tensor-core contraction.  want_matches=False computes the
+    distance matrices only (get_dist_matrix).  tiles0/tiles1: descriptor tile images from
+    `encode(want_tiles=True)` (uniform batches with n % 128 == 0)."""
     _req_cuda(desc0, "desc0")
     _req_cuda(desc1, "desc1")
     dev = desc0.device
@@ -145,20 +172,22 @@ def match_descriptors(desc0, desc1, layout, n_pairs, nn_thresh, mutual=True, *, 
     mx0 = max_n0 if varlen else n0
     mx1 = max_n1 if varlen else n1
     mk0, mk1 = (max_k0, max_k1) if seg else (mx0, mx1)
+    total_n0 = int(desc0.numel() // d) if varlen else n_pairs * n0
+    total_n1 = int(desc1.numel() // d) if varlen else n_pairs * n1
     if total_k0 is None:
-        total_k0 = n_pairs * n0 if not varlen else int(desc0.numel() // d)
-        total_k1 = n_pairs * n1 if not varlen else int(desc1.numel() // d)
+        total_k0, total_k1 = total_n0, total_n1
+    if seg or d != 256:
+        want_dist = True
     stride = mk0 * mk1
     i32 = dict(dtype=torch.int32, device=dev)
     f32 = dict(dtype=torch.float32, device=dev)
-    out = {
-        "matches0": torch.empty(max(total_k0, 1), **i32)[:total_k0],
-        "scores0": torch.empty(max(total_k0, 1), **f32)[:total_k0],
-        "nn1": torch.empty(max(total_k1, 1), **i32)[:total_k1],
-        "counts": (torch.zeros if n_pairs == 0 else torch.empty)(max(n_pairs, 1), **i32)[:n_pairs],   # zeroed by the kernels
-        "dist_key": torch.empty(max(n_pairs * stride, 1), **f32)[:n_pairs * stride],
-        "stride": stride,
-    }
+    out = {"stride": stride}
+    if want_matches:
+        out["matches0"] = torch.empty(max(total_k0, 1), **i32)[:total_k0]
+        out["scores0"] = torch.empty(max(total_k0, 1), **f32)[:total_k0]
+        out["nn1"] = torch.empty(max(total_k1, 1), **i32)[:total_k1]
+        out["counts"] = (torch.zeros if n_pairs == 0 else torch.empty)(max(n_pairs, 1), **i32)[:n_pairs]   # zeroed by the kernels
+    out["dist_key"] = torch.empty(max(n_pairs * stride, 1), **f32)[:n_pairs * stride] if want_dist else None
     if n_pairs == 0:
         return out
     dist_sub = torch.empty(max(n_pairs * mx0 * mx1, 1), **f32) if seg else None
@@ -166,12 +195,21 @@ def match_descriptors(desc0, desc1, layout, n_pairs, nn_thresh, mutual=True, *, 
     tensors = [(_i32c(t) if t is not None else None) for t in tensors]
     inp = N.LtrMatchInput(desc0.data_ptr(), desc1.data_ptr(), int(layout), int(d), int(n_pairs), int(n0), int(n1),
                           *[t.data_ptr() if t is not None else None for t in tensors],
-                          int(max_n0), int(max_n1), int(max_k0), int(max_k1), 0, float(nn_thresh), int(bool(mutual)))
-    o = N.LtrMatchOutput(out["matches0"].data_ptr(), out["scores0"].data_ptr(), out["nn1"].data_ptr(),
-                         out["counts"].data_ptr(), out["dist_key"].data_ptr(),
-                         dist_sub.data_ptr() if dist_sub is not None else None)
+                          int(max_n0), int(max_n1), int(max_k0), int(max_k1), 0, float(nn_thresh), int(bool(mutual)),
+                          int(total_n0), int(total_n1), int(dist_mode),
+                          tiles0.data_ptr() if tiles0 is not None else None,
+                          tiles1.data_ptr() if tiles1 is not None else None,
+                          int(tiles_lines[0]), int(tiles_lines[1]), int(tiles_row0[0]), int(tiles_row0[1]))
+    lib = N.load()
+    need = int(lib.ltr_match_workspace_bytes(C.byref(inp)))
+    if need < 0:
+        N.check(need, "ltr_match_workspace_bytes")
+    ws = _match_workspace(dev, need)
+    g = lambda k: out[k].data_ptr() if out.get(k) is not None else None
+    o = N.LtrMatchOutput(g("matches0"), g("scores0"), g("nn1"), g("counts"), g("dist_key"),
+                         dist_sub.data_ptr() if dist_sub is not None else None, ws.data_ptr(), ws.numel())
     with torch.cuda.device(dev):
-        rc = N.load().ltr_match(C.byref(inp), C.byref(o), dev.index, _stream_ptr(dev))
+        rc = lib.ltr_match(C.byref(inp), C.byref(o), dev.index, _stream_ptr(dev))
     N.check(rc, "ltr_match")
     return out
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -24,8 +25,7 @@ int set_error(int code, const std::string& msg);
 enum KernelClass : int {
   KC_SMALL_MLP = 0,
   KC_LINEAR,
-  KC_CLS_POOL,
-  KC_LAYERNORM,
+  KC_IMG_CONVERT,
   KC_SIG_ATTN,
   KC_FINAL_NORM,
   KC_DIST,
@@ -33,20 +33,26 @@ enum KernelClass : int {
   KC_ARGMIN,
   KC_MUTUAL,
   KC_TOKEN_FUSED,
-  KC_LINE_FUSED,
-  KC_SIG_FUSED,
   KC_TOKENIZE,
+  KC_DESC_TILES,
+  KC_MATCH_TC,
+  KC_MATCH_TAIL,
   KC_COUNT
 };
 const char* kernel_class_name(int kc);
 
 extern std::atomic<int64_t> g_launches;
 
+// Threading contract of the C ABI: any number of host threads may call into the library
+// concurrently (e.g. one thread per GPU); the process-wide state below is guarded by g_state_mutex.
+// Per-class profiling (ltr_profile_*) is a process-wide switch: arm it, run, read it - from one thread.
+extern std::mutex g_state_mutex;
+
 struct Profiler {
-  bool on = false;
+  std::atomic<bool> on{false};
   struct Rec { int kc; cudaEvent_t a, b; };
-  std::vector<Rec> recs;
-  std::vector<cudaEvent_t> pool;
+  std::vector<Rec> recs;          // guarded by g_state_mutex
+  std::vector<cudaEvent_t> pool;  // guarded by g_state_mutex
   cudaEvent_t get();
 };
 extern Profiler g_prof;
@@ -55,18 +61,19 @@ extern Profiler g_prof;
 // CUDA events on the launching stream (so the measurement sees exactly that kernel).
 struct LaunchScope {
   cudaStream_t s;
-  int idx = -1;
+  cudaEvent_t end = nullptr;
   LaunchScope(int kc, cudaStream_t stream) : s(stream) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (g_prof.on) {
+    if (g_prof.on.load(std::memory_order_relaxed)) {
+      std::lock_guard<std::mutex> lk(g_state_mutex);
       Profiler::Rec r{kc, g_prof.get(), g_prof.get()};
       cudaEventRecord(r.a, s);
       g_prof.recs.push_back(r);
-      idx = (int)g_prof.recs.size() - 1;
+      end = r.b;
     }
   }
   ~LaunchScope() {
-    if (idx >= 0) cudaEventRecord(g_prof.recs[idx].b, s);
+    if (end) cudaEventRecord(end, s);
   }
 };
 
@@ -122,13 +129,15 @@ __device__ __forceinline__ void image_range(const int* __restrict__ cu, int lpi,
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device AND per kernel: remember the
 // (kernel address, device) pairs already configured.  (Kernels sharing a signature share the
 // template instantiation below, so the cache must be keyed by the function pointer.)
+extern std::vector<std::pair<const void*, int>> g_smem_configured;   // guarded by g_state_mutex
 template <typename K>
 inline cudaError_t ensure_dynamic_smem(K kernel, int bytes) {
-  static std::vector<std::pair<const void*, int>> done;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   const void* key = reinterpret_cast<const void*>(kernel);
+  std::lock_guard<std::mutex> lk(g_state_mutex);
+  auto& done = g_smem_configured;
   for (auto& d : done)
     if (d.first == key && d.second == dev) return cudaSuccess;
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

@@ -43,7 +43,7 @@ small_mlp_kernel(SmallMlpWeights w, const float* __restrict__ in0, const float* 
                  const float* __restrict__ in2, ActImg out, int rows, float cx, float cy,
                  float scale) {
   constexpr int IN = TOKEN ? 3 : 5;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   auto& S = *reinterpret_cast<SmallMlpSmem<IN>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_launch_dependents();

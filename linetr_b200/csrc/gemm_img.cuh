@@ -59,9 +59,12 @@ struct GemmImgCfg {
   static constexpr int OFF_BAR = OFF_STG + 8 * STG_WARP;
   static constexpr int OFF_XCH = OFF_BAR + 256;                     // row-norm partial sums [2][2][128] fp32 (BN = 256 only)
   static constexpr int XCH = BN == 256 ? 2048 : 0;
-  // 227 KB is the CTA limit: with the exchange buffer the BN = 256 variant keeps 768 B of alignment
-  // slack (the dynamic window starts 1024-aligned in practice; a larger pad would fault loudly)
+  // the dynamic window is declared __align__(1024) (no static shared memory in this kernel, so it starts
+  // at the CTA's 1 KB-aligned window base); the in-kernel round-up is then a no-op and the slack below
+  // is never consumed - it only keeps the carve-up valid should a toolchain ever place the window at a
+  // smaller alignment (BN = 256 has 768 B left under the 227 KB CTA limit)
   static constexpr int SMEM = OFF_XCH + XCH + (BN == 256 ? 768 : 1024);
+  static_assert(SMEM <= 232448, "gemm_img: shared memory budget (227 KB per CTA)");
   static constexpr int TMEM_COLS = 2 * BN;        // two accumulators
   static constexpr int THREADS = 320;             // TMA warp, MMA warp, 8 epilogue warps
 };
@@ -260,10 +263,9 @@ __device__ __forceinline__ void epi_norm_tile(const GemmImgArgs& p, uint32_t tme
 template <int BN>
 __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
   using Cfg = GemmImgCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  if (BN == 256 && ((1024u - (raw & 1023u)) & 1023u) > 768u) __trap();   // see GemmImgCfg::SMEM
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
@@ -458,15 +460,17 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
 }
 
 inline int device_sm_count() {
-  static int sms[64] = {0};
+  static std::atomic<int> sms[64];   // zero-initialised; benign duplicate queries, no torn state
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return 148;
-  if (!sms[dev]) {
-    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (sms[dev] <= 0) sms[dev] = 148;
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    sms[dev].store(v, std::memory_order_relaxed);
   }
-  return sms[dev];
+  return v;
 }
 
 template <int BN>

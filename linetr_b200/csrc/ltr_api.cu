@@ -1,6 +1,7 @@
 // C ABI of linetr_b200 (see include/linetr_b200.h): checkpoint folding/packing, workspace
 // carving and the launch sequence of the line-descriptor forward and the matcher.
 #include "../../include/linetr_b200.h"
+#include "../../include/linetr_b200_debug.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -16,12 +17,15 @@
 #include "sig_attention_tc.cuh"
 #include "tokenizer_kernels.cuh"
 #include "match_kernels.cuh"
+#include "match_tc.cuh"
 
 namespace ltr {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
 Profiler g_prof;
+std::mutex g_state_mutex;
+std::vector<std::pair<const void*, int>> g_smem_configured;
 
 int set_error(int code, const std::string& msg) {
   g_last_error = msg;
@@ -29,9 +33,9 @@ int set_error(int code, const std::string& msg) {
 }
 
 const char* kernel_class_name(int kc) {
-  static const char* names[KC_COUNT] = {"small_mlp", "linear", "cls_pool", "layernorm", "sig_attention",
-                                         "final_norm", "dist", "segmean", "argmin", "mutual",
-                                         "token_fused", "line_fused", "sig_fused", "tokenize"};
+  static const char* names[KC_COUNT] = {"small_mlp", "linear", "img_convert", "sig_attention", "final_norm",
+                                         "dist", "segmean", "argmin", "mutual", "token_fused",
+                                         "tokenize", "desc_tiles", "match_tc", "match_tail"};
   return (kc >= 0 && kc < KC_COUNT) ? names[kc] : "?";
 }
 
@@ -47,10 +51,8 @@ cudaEvent_t Profiler::get() {
 }
 
 // ------------------------------------------------------------------ packed model
-// One wide linear layer: fp32 weights (CUDA-core engine) and the packed split-bf16 image
-// (tensor-core engine) of the same folded matrix.
+// One wide linear layer: fp32 bias and the packed split-bf16 tile image of the folded matrix.
 struct Lin {
-  const float* w = nullptr;
   const float* b = nullptr;
   TcWeight tw;
 };
@@ -62,8 +64,7 @@ struct MlpTail {  // positional encoder: narrow head + the two wide layers (128-
 
 struct SigLayer {
   Lin qkv;    // [768,256] head-major rows, q rows pre-scaled by 1/8
-  Lin merge;  // [256,256] input columns head-major
-  Lin mlp1;   // [512,512] BN folded
+  Lin mlp1;   // [512,512] BN folded, attention output projection (`merge`) folded into the o-half
   Lin mlp2;   // [256,512]
 };
 
@@ -86,7 +87,7 @@ namespace ltr {
 
 using TensorMap = std::unordered_map<std::string, std::pair<const float*, int64_t>>;
 
-struct LinOff { size_t w, b, tc; int N, K; };
+struct LinOff { size_t b, tc; int N, K; };
 
 struct HostPack {
   std::vector<float> buf;
@@ -97,10 +98,10 @@ struct HostPack {
     for (size_t i = 0; i < v.size(); ++i) buf[off + i] = (float)v[i];
     return off;
   }
-  // wide layer [N,K]: fp32 copy + tensor-core image.  `groups` > 1 packs row groups of N/groups
-  // rows as independent matrices (the per-head V projection).
+  // wide layer [N,K]: bias + tensor-core image.  `groups` > 1 packs row groups of N/groups
+  // rows as independent matrices.
   LinOff add_lin(const std::vector<double>& W, const std::vector<double>& b, int N, int K, int groups = 1) {
-    LinOff o{add(W), add(b), 0, N, K};
+    LinOff o{add(b), 0, N, K};
     size_t off = (tc.size() + 511) / 512 * 512;  // 1024-byte alignment
     tc.resize(off + 2 * (size_t)N * K);
     const int gn = N / groups;
@@ -114,7 +115,6 @@ struct HostPack {
 
 static Lin bind_lin(const LinOff& o, float* fbase, uint16_t* tbase, int groups = 1) {
   Lin l;
-  l.w = fbase + o.w;
   l.b = fbase + o.b;
   l.tw.hi = reinterpret_cast<const __nv_bfloat16*>(tbase + o.tc);
   l.tw.lo = reinterpret_cast<const __nv_bfloat16*>(tbase + o.tc + (size_t)o.N * o.K);
@@ -221,12 +221,12 @@ static EncodeWs carve(const LtrModel* m, int n_lines, int T, char* base) {
     a.kblocks = K / 64;
     return a;
   };
-  (void)m; (void)T;
+  (void)T;
   const int64_t R = n_lines;
   w.z = takei(R, 1024);
   w.ctx = takei(R, 256);
   w.y1i = takei(R, 256);
-  w.g = takei(R, 1024);
+  w.g = takei(R, m->cfg.d_inner);   // FFN hidden activation [R, d_inner]
   w.l128 = takei(R, 128);
   w.l256 = takei(R, 256);
   w.y1 = takef(R * 256);
@@ -296,8 +296,17 @@ static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const fl
     if (_rc != 0) return _rc; \
   } while (0)
 
-static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, float* out_rows, const EncodeWs& w,
-                       cudaStream_t s) {
+static ActImg tiles_image(void* tiles, int64_t n_lines) {
+  ActImg a;
+  const int64_t plane = align_up(n_lines, 128) * MT_D;   // bf16 elements per plane
+  a.hi = reinterpret_cast<__nv_bfloat16*>(tiles);
+  a.lo = a.hi + plane;
+  a.kblocks = MT_KB;
+  return a;
+}
+
+static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, float* out_rows, void* out_tiles,
+                       const EncodeWs& w, cudaStream_t s) {
   const int R = in.n_lines, T = in.n_tokens;
   const int* cu = in.cu_lines_dev;
   // ---- token stage: one fused persistent kernel (narrow MLP, 3 tensor-core layers, + desc, CLS pooling) ----
@@ -339,8 +348,11 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
     // ~2^-17 relative precision; an fp32 copy would double the store traffic of this epilogue)
     LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, nullptr, 0, &w.xm, 0, nullptr, 0, &w.xm, 0));
   }
-  if (!out_cf) {   // rows only: projection + L2 normalisation in one launch
-    LTR_TRY(gemm_norm(m->wf, w.xm, R, s, NORM_L2, nullptr, nullptr, nullptr, 0, nullptr, 0, out_rows, 256, nullptr, 0));
+  if (!out_cf) {   // rows (+ matcher tile image): projection + L2 normalisation in one launch
+    ActImg tiles{};
+    if (out_tiles) tiles = tiles_image(out_tiles, R);
+    LTR_TRY(gemm_norm(m->wf, w.xm, R, s, NORM_L2, nullptr, nullptr, nullptr, 0, nullptr, 0, out_rows, 256,
+                      out_tiles ? &tiles : nullptr, 0));
     return 0;
   }
   LTR_TRY(gemm(m->wf, w.xm, 0, R, ACT_NONE, s, w.yf, 256));
@@ -480,7 +492,7 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   size_t oL2g = hp.add(vec(ln2g, D)), oL2b = hp.add(vec(ln2b, D));
 
   // ---- signature layers ----
-  struct SigOff { LinOff qkv, merge, mlp1, mlp2; };
+  struct SigOff { LinOff qkv, mlp1, mlp2; };
   std::vector<SigOff> so(cfg->n_sig_layers);
   for (int li = 0; li < cfg->n_sig_layers; ++li) {
     const std::string p = "selfattn.layers." + std::to_string(li);
@@ -525,8 +537,7 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
       for (int i = 0; i < D; ++i) bacc += W1[(size_t)o * 2 * D + D + i] * (double)bm[i];
       B1f[o] = bacc;
     }
-    so[li] = {hp.add_lin(Wqkv, bqkv, 768, D), hp.add_lin(Wm, vec(bm, D), D, D), hp.add_lin(W1f, B1f, 2 * D, 2 * D),
-              hp.add_lin(W2, B2, D, 2 * D)};
+    so[li] = {hp.add_lin(Wqkv, bqkv, 768, D), hp.add_lin(W1f, B1f, 2 * D, 2 * D), hp.add_lin(W2, B2, D, 2 * D)};
   }
   std::vector<double> Wf, Bf;
   if (!fold_layer(tm, "final_proj", "", D, D, Wf, Bf, err)) return set_error(LTR_E_INVALID, err);
@@ -558,7 +569,7 @@ int ltr_create(const LtrTensor* tensors, int32_t n_tensors, const LtrConfig* cfg
   m->w2 = bind_lin(oW2, B, TB);
   m->ln2g = B + oL2g; m->ln2b = B + oL2b;
   for (auto& o : so)
-    m->sig.push_back({bind_lin(o.qkv, B, TB), bind_lin(o.merge, B, TB), bind_lin(o.mlp1, B, TB), bind_lin(o.mlp2, B, TB)});
+    m->sig.push_back({bind_lin(o.qkv, B, TB), bind_lin(o.mlp1, B, TB), bind_lin(o.mlp2, B, TB)});
   m->wf = bind_lin(oWf, B, TB);
   *out = m;
   return LTR_OK;
@@ -578,9 +589,14 @@ int64_t ltr_encode_workspace_bytes(const LtrModel* m, int32_t n_images, int32_t 
   return carve(m, n_lines, n_tokens, nullptr).bytes + 256;
 }
 
-int ltr_encode(LtrModel* m, const LtrEncodeInput* in, float* desc_cf_out, float* desc_rows_out, void* workspace,
-               int64_t workspace_bytes, void* stream) {
-  if (!m || !in) return set_error(LTR_E_INVALID, "ltr_encode: null argument");
+int64_t ltr_desc_tiles_bytes(int32_t n_lines) {
+  if (n_lines < 0) return set_error(LTR_E_INVALID, "ltr_desc_tiles_bytes: bad argument");
+  return align_up(n_lines, 128) * MT_D * 2 * 2;   // hi + lo plane, bf16
+}
+
+int ltr_encode(LtrModel* m, const LtrEncodeInput* in, const LtrEncodeOutput* out, void* workspace, int64_t workspace_bytes,
+               void* stream) {
+  if (!m || !in || !out) return set_error(LTR_E_INVALID, "ltr_encode: null argument");
   if (in->n_lines == 0 || in->n_images == 0) return LTR_OK;
   if (in->n_tokens < 1 || in->n_tokens > 128) return set_error(LTR_E_UNSUPPORTED, "ltr_encode: n_tokens must be in 1..128");
   if (!in->sublines || !in->resp || !in->angle || !in->pnt || !in->desc || !in->score)
@@ -592,49 +608,190 @@ int ltr_encode(LtrModel* m, const LtrEncodeInput* in, float* desc_cf_out, float*
   if (in->cu_lines_host && (in->cu_lines_host[0] != 0 || in->cu_lines_host[in->n_images] != in->n_lines))
     return set_error(LTR_E_INVALID, "ltr_encode: cu_lines must start at 0 and end at n_lines");
   if (!(in->image_width > 0.f) || !(in->image_height > 0.f)) return set_error(LTR_E_INVALID, "ltr_encode: bad image shape");
+  if (out->desc_tiles && (out->desc_cf || !out->desc_rows))
+    return set_error(LTR_E_UNSUPPORTED, "ltr_encode: desc_tiles needs desc_rows and no desc_cf");
+  if (out->desc_tiles && (reinterpret_cast<uintptr_t>(out->desc_tiles) & 15))
+    return set_error(LTR_E_INVALID, "ltr_encode: desc_tiles must be 16-byte aligned");
   LTR_CUDA_TRY(cudaSetDevice(m->device));
   char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(workspace), 256));
   EncodeWs w = carve(m, in->n_lines, in->n_tokens, base);
   if (!workspace || (base - (char*)workspace) + w.bytes > workspace_bytes)
     return set_error(LTR_E_WORKSPACE, "ltr_encode: workspace too small, need " + std::to_string(w.bytes + 256));
-  return encode_impl(m, *in, desc_cf_out, desc_rows_out, w, as_stream(stream));
+  return encode_impl(m, *in, out->desc_cf, out->desc_rows, out->desc_tiles, w, as_stream(stream));
+}
+
+// ---- tensor-core matcher plumbing (d == 256) ----
+struct MatchPlan {
+  int mx[2], tmax[2], total[2];
+  bool direct[2];       // side uses the caller's tile image (written by ltr_encode)
+  ActImg img[2];
+  uint2* slot[2];
+  float* sq[2];
+  int64_t bytes;
+};
+
+static MatchPlan plan_match(const LtrMatchInput& in, char* base) {
+  MatchPlan pl{};
+  const int P = in.n_pairs;
+  const int n[2] = {in.n0, in.n1};
+  const int mxn[2] = {in.max_n0, in.max_n1};
+  const int tot[2] = {in.total_n0, in.total_n1};
+  const void* tiles[2] = {in.tiles0, in.tiles1};
+  const int tl[2] = {in.tiles_lines0, in.tiles_lines1};
+  const int tr0[2] = {in.tiles_row0_0, in.tiles_row0_1};
+  const bool varlen = in.cu0 != nullptr;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    char* p = base + off;
+    off = align_up(off + bytes, 1024);
+    return p;
+  };
+  for (int s = 0; s < 2; ++s) {
+    pl.mx[s] = varlen ? mxn[s] : n[s];
+    pl.tmax[s] = cdiv(pl.mx[s], 128);
+    pl.total[s] = varlen ? tot[s] : P * n[s];
+    pl.direct[s] = tiles[s] && !varlen && in.dist_mode == 0 && n[s] % 128 == 0 && tr0[s] % 128 == 0 && tr0[s] >= 0 &&
+                   (int64_t)tr0[s] + (int64_t)P * n[s] <= align_up(tl[s], 128);
+    if (pl.direct[s]) {
+      pl.img[s] = tiles_image(const_cast<void*>(tiles[s]), tl[s]);
+    } else {
+      const int64_t plane = (int64_t)P * pl.tmax[s] * 128 * MT_D;   // bf16 elements
+      pl.img[s].hi = reinterpret_cast<__nv_bfloat16*>(take(plane * 2));
+      pl.img[s].lo = reinterpret_cast<__nv_bfloat16*>(take(plane * 2));
+      pl.img[s].kblocks = MT_KB;
+    }
+    pl.slot[s] = reinterpret_cast<uint2*>(take((int64_t)std::max(pl.total[s], 1) * 8));
+    pl.sq[s] = in.dist_mode == 1 ? reinterpret_cast<float*>(take((int64_t)std::max(pl.total[s], 1) * 4)) : nullptr;
+  }
+  pl.bytes = off;
+  return pl;
+}
+
+static const char* check_match_input(const LtrMatchInput* in) {
+  if (in->d <= 0 || in->d % 16) return "ltr_match: descriptor dim must be a multiple of 16";
+  const bool seg = in->sub_off0 != nullptr || in->sub_off1 != nullptr;
+  if (seg && (!in->sub_off0 || !in->sub_off1 || !in->cuk0 || !in->cuk1 || !in->cu0 || !in->cu1))
+    return "ltr_match: keyline merging needs sub_off0/1, cuk0/1 and cu0/1";
+  if ((in->cu0 == nullptr) != (in->cu1 == nullptr)) return "ltr_match: cu0/cu1 must be given together";
+  if (in->dist_mode != 0 && in->dist_mode != 1) return "ltr_match: dist_mode must be 0 or 1";
+  if (in->dist_mode == 1 && (in->d != MT_D || seg)) return "ltr_match: dist_mode 1 needs d == 256 and no keyline merging";
+  if (in->d == MT_D && in->cu0 && (in->total_n0 < 0 || in->total_n1 < 0)) return "ltr_match: total_n0/total_n1 required with cu0/cu1";
+  return nullptr;
+}
+
+}  // extern "C"
+
+// launch sequence of the tensor-core matcher; returns 0 or an error code
+static int run_match_tc(const LtrMatchInput& in, const LtrMatchOutput& out, const MatchPlan& pl, bool seg, long long stride_key,
+                        cudaStream_t s) {
+  const int P = in.n_pairs;
+  const bool want_nn = out.matches0 != nullptr && !seg;
+  const bool both = want_nn && in.mutual;
+  if (pl.mx[0] > 0 && pl.mx[1] > 0) {
+    if (!pl.direct[0] || !pl.direct[1]) {
+      DescTilesArgs da{};
+      da.layout = in.layout;
+      const float* d[2] = {in.desc0, in.desc1};
+      const int* cu[2] = {in.cu0, in.cu1};
+      const int n[2] = {in.n0, in.n1};
+      int tm = 0;
+      for (int sd = 0; sd < 2; ++sd) {
+        da.d[sd] = d[sd]; da.cu[sd] = cu[sd]; da.n[sd] = n[sd]; da.img[sd] = pl.img[sd];
+        da.tmax[sd] = pl.direct[sd] ? 0 : pl.tmax[sd];
+        da.sq[sd] = pl.sq[sd];
+        tm = std::max(tm, da.tmax[sd]);
+      }
+      LaunchScope ls(KC_DESC_TILES, s);
+      LTR_CUDA_TRY(launch_pdl(desc_tiles_kernel, dim3(tm * 4, P, 2), dim3(256), 0, s, da));
+    }
+    MatchTcArgs ma{};
+    const int* cu[2] = {in.cu0, in.cu1};
+    const int n[2] = {in.n0, in.n1};
+    const int tr0[2] = {in.tiles_row0_0, in.tiles_row0_1};
+    for (int sd = 0; sd < 2; ++sd) {
+      ma.s[sd].img = pl.img[sd]; ma.s[sd].cu = cu[sd]; ma.s[sd].n = n[sd];
+      ma.s[sd].tile_mode = pl.direct[sd] ? 1 : 0; ma.s[sd].tile_row0 = pl.direct[sd] ? tr0[sd] : 0;
+      ma.s[sd].tmax = pl.tmax[sd]; ma.s[sd].sq = pl.sq[sd]; ma.s[sd].slot = pl.slot[sd];
+    }
+    ma.dist_mode = in.dist_mode;
+    ma.dist = seg ? out.dist_sub : out.dist_key;
+    ma.dist_stride = seg ? (long long)pl.mx[0] * pl.mx[1] : stride_key;
+    ma.counts = want_nn ? out.counts : nullptr;
+    ma.n_pairs = P;
+    LTR_CUDA_TRY(ensure_dynamic_smem(match_tc_kernel, MT_SMEM));
+    LaunchScope ls(KC_MATCH_TC, s);
+    LTR_CUDA_TRY(launch_pdl(match_tc_kernel, dim3(pl.tmax[0] + (both ? pl.tmax[1] : 0), P), dim3(MT_THREADS), (size_t)MT_SMEM, s, ma));
+  } else if (want_nn) {
+    LTR_CUDA_TRY(cudaMemsetAsync(out.counts, 0, sizeof(int) * P, s));
+  }
+  if (want_nn && pl.mx[0] > 0) {
+    MatchTailArgs ta{};
+    ta.d[0] = in.desc0; ta.d[1] = in.desc1; ta.layout = in.layout;
+    ta.cu[0] = in.cu0; ta.cu[1] = in.cu1; ta.n[0] = in.n0; ta.n[1] = in.n1;
+    ta.sq[0] = pl.sq[0]; ta.sq[1] = pl.sq[1]; ta.dist_mode = in.dist_mode;
+    ta.slot[0] = pl.slot[0]; ta.slot[1] = pl.slot[1];
+    ta.thr = in.nn_thresh; ta.mutual = in.mutual;
+    ta.matches0 = out.matches0; ta.scores0 = out.scores0; ta.nn1 = out.nn1; ta.counts = out.counts;
+    ta.max0 = pl.mx[0];
+    LaunchScope ls(KC_MATCH_TAIL, s);
+    LTR_CUDA_TRY(launch_pdl(match_tail_kernel, dim3(cdiv(pl.mx[0] + (in.mutual ? pl.mx[1] : 0), 8), P), dim3(256), 0, s, ta));
+  }
+  return 0;
+}
+
+extern "C" {
+
+int64_t ltr_match_workspace_bytes(const LtrMatchInput* in) {
+  if (!in) return set_error(LTR_E_INVALID, "ltr_match_workspace_bytes: null argument");
+  if (const char* e = check_match_input(in)) return set_error(LTR_E_INVALID, e);
+  if (in->n_pairs <= 0 || in->d != MT_D) return 0;
+  return plan_match(*in, nullptr).bytes + 1024;
 }
 
 int ltr_match(const LtrMatchInput* in, const LtrMatchOutput* out, int32_t device, void* stream) {
   if (!in || !out) return set_error(LTR_E_INVALID, "ltr_match: null argument");
   if (in->n_pairs <= 0) return LTR_OK;
-  if (!out->matches0 || !out->scores0 || !out->nn1 || !out->counts || !out->dist_key)
-    return set_error(LTR_E_INVALID, "ltr_match: matches0, scores0, nn1, counts and dist_key are required");
-  if (in->d <= 0 || in->d % 16) return set_error(LTR_E_UNSUPPORTED, "ltr_match: descriptor dim must be a multiple of 16");
-  const bool seg = in->sub_off0 != nullptr || in->sub_off1 != nullptr;
-  if (seg && (!in->sub_off0 || !in->sub_off1 || !in->cuk0 || !in->cuk1 || !in->cu0 || !in->cu1 || !out->dist_sub))
-    return set_error(LTR_E_INVALID, "ltr_match: keyline merging needs sub_off0/1, cuk0/1, cu0/1 and dist_sub");
-  if ((in->cu0 == nullptr) != (in->cu1 == nullptr)) return set_error(LTR_E_INVALID, "ltr_match: cu0/cu1 must be given together");
+  if (const char* e = check_match_input(in)) return set_error(in->d % 16 ? LTR_E_UNSUPPORTED : LTR_E_INVALID, e);
+  const bool seg = in->sub_off0 != nullptr;
+  const bool tc = in->d == MT_D;
+  const bool want_nn = out->matches0 != nullptr;
+  if (want_nn && (!out->scores0 || !out->nn1 || !out->counts))
+    return set_error(LTR_E_INVALID, "ltr_match: matches0 needs scores0, nn1 and counts");
+  if (!want_nn && !out->dist_key) return set_error(LTR_E_INVALID, "ltr_match: nothing to compute (matches0 and dist_key are NULL)");
+  if (seg && (!out->dist_sub || !out->dist_key)) return set_error(LTR_E_INVALID, "ltr_match: keyline merging needs dist_sub and dist_key");
+  if (!tc && !out->dist_key) return set_error(LTR_E_INVALID, "ltr_match: dist_key is required when d != 256");
   LTR_CUDA_TRY(cudaSetDevice(device));
   cudaStream_t s = as_stream(stream);
   const int mx0 = in->cu0 ? in->max_n0 : in->n0, mx1 = in->cu1 ? in->max_n1 : in->n1;
   const int mk0 = seg ? in->max_k0 : mx0, mk1 = seg ? in->max_k1 : mx1;
   const long long stride_key = in->dist_pair_stride > 0 ? in->dist_pair_stride : (long long)mk0 * mk1;
-  if (mx0 > 0 && mx1 > 0) {
-    if (!in->desc0 || !in->desc1) return set_error(LTR_E_INVALID, "ltr_match: null descriptors");
+  if (mx0 > 0 && mx1 > 0 && (!in->desc0 || !in->desc1)) return set_error(LTR_E_INVALID, "ltr_match: null descriptors");
+  if (tc) {
+    char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(out->workspace), 1024));
+    MatchPlan pl = plan_match(*in, base);
+    if (pl.bytes > 0 && (!out->workspace || (base - (char*)out->workspace) + pl.bytes > out->workspace_bytes))
+      return set_error(LTR_E_WORKSPACE, "ltr_match: workspace too small, need " + std::to_string(pl.bytes + 1024));
+    LTR_TRY(run_match_tc(*in, *out, pl, seg, stride_key, s));
+    if (!seg) return LTR_OK;
+  } else if (mx0 > 0 && mx1 > 0) {
+    // generic descriptor dimension: fp32 FMA distance tiles
     DistArgs da{};
     da.d0 = in->desc0; da.d1 = in->desc1; da.layout = in->layout; da.d = in->d;
     da.cu0 = in->cu0; da.cu1 = in->cu1; da.n0 = in->n0; da.n1 = in->n1;
     da.out = seg ? out->dist_sub : out->dist_key;
     da.stride = seg ? (long long)mx0 * mx1 : stride_key;
     dim3 grid(cdiv(mx0, DK_BM), cdiv(mx1, DK_BN), in->n_pairs);
-    {
-      LaunchScope ls(KC_DIST, s);
-      if (in->layout == LTR_LAYOUT_CHANNEL_FIRST) LTR_CUDA_TRY(launch_pdl(dist_kernel<true>, grid, dim3(DK_THREADS), 0, s, da));
-      else LTR_CUDA_TRY(launch_pdl(dist_kernel<false>, grid, dim3(DK_THREADS), 0, s, da));
-    }
-    if (seg && mk0 > 0 && mk1 > 0) {
-      SegMeanArgs sa{out->dist_sub, (long long)mx0 * mx1, out->dist_key, stride_key, in->cuk0, in->cuk1, in->sub_off0, in->sub_off1};
-      LaunchScope ls(KC_SEGMEAN, s);
-      segmean_kernel<<<dim3(cdiv(mk1, 32), cdiv(mk0, 8), in->n_pairs), 256, 0, s>>>(sa);
-      LTR_CUDA_TRY(cudaGetLastError());
-    }
+    LaunchScope ls(KC_DIST, s);
+    if (in->layout == LTR_LAYOUT_CHANNEL_FIRST) LTR_CUDA_TRY(launch_pdl(dist_kernel<true>, grid, dim3(DK_THREADS), 0, s, da));
+    else LTR_CUDA_TRY(launch_pdl(dist_kernel<false>, grid, dim3(DK_THREADS), 0, s, da));
   }
+  if (seg && mx0 > 0 && mx1 > 0 && mk0 > 0 && mk1 > 0) {
+    SegMeanArgs sa{out->dist_sub, (long long)mx0 * mx1, out->dist_key, stride_key, in->cuk0, in->cuk1, in->sub_off0, in->sub_off1};
+    LaunchScope ls(KC_SEGMEAN, s);
+    segmean_kernel<<<dim3(cdiv(mk1, 32), cdiv(mk0, 8), in->n_pairs), 256, 0, s>>>(sa);
+    LTR_CUDA_TRY(cudaGetLastError());
+  }
+  if (!want_nn) return LTR_OK;
   NNArgs na{};
   na.dist = out->dist_key; na.stride = stride_key;
   na.cuk0 = seg ? in->cuk0 : in->cu0; na.cuk1 = seg ? in->cuk1 : in->cu1;
@@ -733,7 +890,7 @@ static int linear_img_impl(const float* x, int32_t ldx, const float* w_host, con
     ActImg A{reinterpret_cast<__nv_bfloat16*>(da), reinterpret_cast<__nv_bfloat16*>(da + mpad * k), k / 64};
     ActImg O{reinterpret_cast<__nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dout + mpad * n), n / 64};
     {
-      LaunchScope ls(KC_LAYERNORM, s);
+      LaunchScope ls(KC_IMG_CONVERT, s);
       to_image_kernel<<<cdiv((long long)m * (k / 8), 256), 256, 0, s>>>(x, ldx, m, k, A, 0);
     }
     GemmImgArgs a{};
@@ -745,7 +902,7 @@ static int linear_img_impl(const float* x, int32_t ldx, const float* w_host, con
     a.norm = ns.norm; a.eps = ns.eps; a.ng = ns.g; a.nbeta = ns.beta; a.nadd = ns.add; a.ldadd = ns.ldadd;
     rc = launch_gemm_img(a, s, bn_hint);
     if (rc == 0 && y_from_image) {
-      LaunchScope ls(KC_LAYERNORM, s);
+      LaunchScope ls(KC_IMG_CONVERT, s);
       from_image_kernel<<<cdiv((long long)m * n, 256), 256, 0, s>>>(O, 0, y_from_image, n, m, n);
     }
     ce = cudaStreamSynchronize(s);

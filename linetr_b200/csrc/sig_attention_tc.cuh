@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(ActImg qkv, ActIm
   if (tid == 0) LTR_DBG_STAMP(30);
   pdl_launch_dependents();
 
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* q_hi = smem;                 // [128 x 64]

@@ -72,7 +72,7 @@ __device__ __forceinline__ int xs_index(int row, int col) {
 
 __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, const __grid_constant__ CUtensorMap desc_map) {
   using S = TokenFusedSmem;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* act = smem;

@@ -142,8 +142,8 @@ class PairMatches:
     scores0: torch.Tensor      # float32, distance to the nearest neighbour
     counts: torch.Tensor       # int32 [n_pairs]
     offsets0: np.ndarray       # int32 [n_pairs+1] key-line offsets of side 0 into matches0
-    dist: torch.Tensor         # float32 flat, pair p at p*stride, row-major [K0_p, K1_p]
-    stride: int
+    dist: Optional[torch.Tensor]   # float32 flat, pair p at p*stride, row-major [K0_p, K1_p]; None unless requested
+    stride: int                    # (want_dist=True) or needed for key-line merging
     desc0: Optional[torch.Tensor] = None   # [R0,256] unit descriptors (rows)
     desc1: Optional[torch.Tensor] = None
 
@@ -162,27 +162,39 @@ class PairEngine:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
 
-    def encode(self, batch: LineBatch, want_cf=False) -> torch.Tensor:
-        """-> unit descriptors [R,256] (rows); with want_cf also the flat channel-first layout."""
+    def encode(self, batch: LineBatch, want_cf=False, want_tiles=False):
+        """-> unit descriptors [R,256] (rows); with want_cf also the flat channel-first layout, with
+        want_tiles also the descriptor tile image the tensor-core matcher contracts (`ltr_encode`
+        writes it from the same epilogue as the rows)."""
         h = self.model._get_handle(self.device)
         L = batch.uniform_lines
         kw = dict(lines_per_image=L) if L is not None and L > 0 else dict(
             cu_lines_host=batch.cu_lines, cu_lines_dev=batch.dev_i32("cu_lines", self.device))
-        cf, rows = _ops.encode(h, batch.sublines, batch.resp, batch.angle, batch.pnt, batch.desc, batch.score,
-                               self.model._image_wh(), want_cf=want_cf, want_rows=True, **kw)
-        return (rows, cf) if want_cf else rows
+        res = _ops.encode(h, batch.sublines, batch.resp, batch.angle, batch.pnt, batch.desc, batch.score,
+                          self.model._image_wh(), want_cf=want_cf, want_rows=True, want_tiles=want_tiles, **kw)
+        if want_tiles:
+            return res[1], res[2]
+        return (res[1], res[0]) if want_cf else res[1]
 
     def match_pairs(self, side0: LineBatch, side1: LineBatch, nn_thresh: Optional[float] = None, mutual=True,
-                    keep_desc=False) -> PairMatches:
+                    keep_desc=False, want_dist=False) -> PairMatches:
+        """want_dist=True also returns the key-line distance matrices (`Matching`'s
+        'matching_scores_l'); by default they are never materialised (the row argmin lives in the
+        epilogue of the tensor-core contraction) unless key-line merging needs them."""
         if side0.n_images != side1.n_images:
             raise ValueError("match_pairs: both sides need the same number of images")
         if nn_thresh is None:
             nn_thresh = self.model.config.get("nn_threshold", 0.8)
         P = side0.n_images
-        d0 = self.encode(side0)
-        d1 = self.encode(side1)
         seg = side0.sub_off is not None or side1.sub_off is not None
         L0, L1 = side0.uniform_lines, side1.uniform_lines
+        tiled = not seg and L0 is not None and L1 is not None and L0 % 128 == 0 and L1 % 128 == 0 and L0 > 0 and L1 > 0
+        if tiled:
+            d0, t0 = self.encode(side0, want_tiles=True)
+            d1, t1 = self.encode(side1, want_tiles=True)
+        else:
+            d0 = self.encode(side0)
+            d1 = self.encode(side1)
         kw = {}
         if seg:
             def csr(b):
@@ -200,19 +212,21 @@ class PairEngine:
             off0 = side0.cuk
         elif L0 is not None and L1 is not None:
             kw = dict(n0=L0, n1=L1)
+            if tiled:
+                kw.update(tiles0=t0, tiles1=t1, tiles_lines=(side0.n_lines, side1.n_lines), tiles_row0=(0, 0))
             off0 = side0.cu_lines
         else:
             kw = dict(cu0=side0.dev_i32("cu_lines", self.device), cu1=side1.dev_i32("cu_lines", self.device),
                       max_n0=int(np.diff(side0.cu_lines).max(initial=0)), max_n1=int(np.diff(side1.cu_lines).max(initial=0)),
                       total_k0=side0.n_lines, total_k1=side1.n_lines)
             off0 = side0.cu_lines
-        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, **kw)
+        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, want_dist=want_dist, **kw)
         return PairMatches(out["matches0"], out["scores0"], out["counts"], np.asarray(off0, dtype=np.int32),
                            out["dist_key"], out["stride"], d0 if keep_desc else None, d1 if keep_desc else None)
 
 
     def match_packed(self, batch: LineBatch, n_pairs: int, nn_thresh: Optional[float] = None, mutual=True,
-                     keep_desc=False) -> PairMatches:
+                     keep_desc=False, want_dist=False) -> PairMatches:
         """Same as match_pairs for a batch that holds BOTH sides: images [0, P) are the side-0
         images of the P pairs, images [P, 2P) their side-1 partners.  One `ltr_encode` over all
         2P images (twice the rows per GEMM launch) and one `ltr_match`."""
@@ -221,11 +235,16 @@ class PairEngine:
             raise ValueError("match_packed: batch must hold 2 * n_pairs images")
         if nn_thresh is None:
             nn_thresh = self.model.config.get("nn_threshold", 0.8)
-        rows = self.encode(batch)
         cu = batch.cu_lines
         R0 = int(cu[P])
-        d0, d1 = rows[:R0], rows[R0:]
         L = batch.uniform_lines
+        # uniform 128-aligned images: the encoder's final GEMM writes the matcher's operand tiles itself
+        tiled = batch.sub_off is None and L is not None and L > 0 and L % 128 == 0
+        if tiled:
+            rows, tiles = self.encode(batch, want_tiles=True)
+        else:
+            rows = self.encode(batch)
+        d0, d1 = rows[:R0], rows[R0:]
         if batch.sub_off is not None:
             key = ("packed_split", str(self.device))
             if key not in batch._dev_cache:
@@ -241,6 +260,8 @@ class PairEngine:
             off0 = batch.cuk[:P + 1]
         elif L is not None:
             kw = dict(n0=L, n1=L)
+            if tiled:
+                kw.update(tiles0=tiles, tiles1=tiles, tiles_lines=(batch.n_lines, batch.n_lines), tiles_row0=(0, R0))
             off0 = cu[:P + 1]
         else:
             key = ("packed_split", str(self.device))
@@ -252,10 +273,9 @@ class PairEngine:
                                              total_k0=R0, total_k1=int(cu[-1]) - R0)
             kw = batch._dev_cache[key]
             off0 = cu[:P + 1]
-        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, **kw)
+        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, want_dist=want_dist, **kw)
         return PairMatches(out["matches0"], out["scores0"], out["counts"], np.asarray(off0, dtype=np.int32),
                            out["dist_key"], out["stride"], d0 if keep_desc else None, d1 if keep_desc else None)
-
 
     def match_packed_host(self, host: LineBatch, n_pairs: int, nn_thresh: Optional[float] = None, mutual=True,
                           n_chunks: int = 4):

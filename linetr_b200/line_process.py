@@ -31,7 +31,7 @@ def get_dist_matrix(desc0, desc1):
     dev = torch.device("cuda", torch.cuda.current_device())
     a = torch.from_numpy(desc0).to(dev, non_blocking=True)
     b = torch.from_numpy(desc1).to(dev, non_blocking=True)
-    out = _ops.match_descriptors(a, b, N.LAYOUT_CHANNEL_FIRST, B, 0.0, False, n0=n, n1=m, d=d)
+    out = _ops.match_descriptors(a, b, N.LAYOUT_CHANNEL_FIRST, B, 0.0, False, n0=n, n1=m, d=d, want_matches=False)
     return out["dist_key"].view(B, n, m).cpu().numpy()
 
 

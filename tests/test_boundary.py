@@ -31,7 +31,12 @@ def test_header_symbols_exported():
     lib = ctypes.CDLL(N.lib_path())
     for s in declared:
         assert hasattr(lib, s), f"{s} not exported"
-    assert N.load().ltr_abi_version() == 1
+    dbg = open(os.path.join(ROOT, "include", "linetr_b200_debug.h")).read()
+    declared_dbg = set(re.findall(r"\b(ltr_[a-z_0-9]+)\s*\(", dbg))
+    assert declared_dbg == set(N.DEBUG_SYMBOLS)
+    for s in declared_dbg:
+        assert hasattr(lib, s), f"{s} not exported"
+    assert N.load().ltr_abi_version() == N.ABI_VERSION == 2
 
 
 def test_state_dict_contract():
