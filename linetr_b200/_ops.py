@@ -24,6 +24,13 @@ def _req_cuda(t: torch.Tensor, name: str):
                          "(there is no CPU fallback)")
 
 
+def current_cuda_device() -> torch.device:
+    """Device the host-numpy entry points (nn_matcher*, get_dist_matrix) compute on."""
+    if not torch.cuda.is_available():
+        raise N.LtrError("linetr_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()

@@ -260,6 +260,73 @@ __device__ __forceinline__ void epi_norm_tile(const GemmImgArgs& p, uint32_t tme
   }
 }
 
+// Plain epilogue of one 128 x BN tile: this warp's 32 rows x its half of the BN columns, 32 columns at a
+// time: bias -> activation -> residual (fp32 rows or split-bf16 image) -> fp32 rows and/or image output.
+template <int BN>
+__device__ __forceinline__ void epi_plain_tile(const GemmImgArgs& p, uint32_t tmem_acc, int mt, int nb, int q, int half, int lane,
+                                               float* stg, uint8_t* stgb) {
+  const int row0 = mt * 128 + q * 32;   // first row of this warp
+#pragma unroll 1
+  for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+    float acc[32];
+    ptx::tmem_ld32(tmem_acc + (uint32_t)c0, acc);
+    const int nbase = nb * BN + c0;
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + nbase + j);
+        acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
+      }
+    }
+    // the activation is uniform per launch: branch ONCE per chunk (an if-converted erff per
+    // element costs ~40 instructions even when ReLU/identity is selected)
+    if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    } else if (p.act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+    }
+    if (p.R) epi_add_rows_f32(p.R, p.ldr, row0, nbase, p.M, lane, stg, acc);
+    if (p.Rimg.hi) {
+      // residual from a split-bf16 image: coalesced 16-byte chunk loads -> staging -> own row
+      const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
+      const uint8_t* rhi = reinterpret_cast<const uint8_t*>(p.Rimg.hi + rtoff);
+      const uint8_t* rlo = reinterpret_cast<const uint8_t*>(p.Rimg.lo + rtoff);
+      const int gch0r = (nbase & 63) >> 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = i * 8 + (lane >> 2), cc = lane & 3;
+        uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+        if (row0 + rl < p.M) {
+          const uint32_t off = ptx::sw128_offset(q * 32 + rl, (gch0r + cc) * 8);
+          vh = *reinterpret_cast<const uint4*>(rhi + off);
+          vl = *reinterpret_cast<const uint4*>(rlo + off);
+        }
+        const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
+        *reinterpret_cast<uint4*>(stgb + slot) = vh;
+        *reinterpret_cast<uint4*>(stgb + 2048 + slot) = vl;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int slot = (lane * 4 + (cc ^ ((lane >> 1) & 3))) * 16;
+        const uint4 vh = *reinterpret_cast<const uint4*>(stgb + slot);
+        const uint4 vl = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
+        const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {   // bf16 -> fp32 is a 16-bit shift
+          acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
+          acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
+        }
+      }
+      __syncwarp();
+    }
+    if (p.C) epi_store_rows_f32(p.C, p.ldc, row0, nbase, p.M, lane, stg, acc);
+    if (p.O.hi) epi_store_image(p.O, p.o_kb0, mt, nbase, q, row0, p.M, lane, stgb, acc);
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
   using Cfg = GemmImgCfg<BN>;
@@ -377,7 +444,6 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
       ptx::mbar_wait(&acc_full[buf], aph);
       ptx::tc_fence_after();
       if (tl < 4 && warp == 2 && lane == 0) LTR_STAMP(tl * 16 + 3);
-      const int row0 = mt * 128 + q * 32;   // first row of this warp
       if constexpr (BN == 256) {
         if (p.norm != NORM_NONE) {
           epi_norm_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN, mt, q, half, lane, tl, stg, stgb,
@@ -388,71 +454,175 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
           continue;
         }
       }
-#pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-        float acc[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c0, acc);
-        if (tl < 4 && warp == 2 && lane == 0 && c0 == 0) LTR_STAMP(tl * 16 + 4);
-        const int nbase = nb * BN + c0;
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + nbase + j);
-            acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
-          }
-        }
-        // the activation is uniform per launch: branch ONCE per chunk (an if-converted erff per
-        // element costs ~40 instructions even when ReLU/identity is selected)
-        if (p.act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
-        } else if (p.act == ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
-        }
-        if (p.R) epi_add_rows_f32(p.R, p.ldr, row0, nbase, p.M, lane, stg, acc);
-        if (p.Rimg.hi) {
-          // residual from a split-bf16 image: coalesced 16-byte chunk loads -> staging -> own row
-          const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
-          const uint8_t* rhi = reinterpret_cast<const uint8_t*>(p.Rimg.hi + rtoff);
-          const uint8_t* rlo = reinterpret_cast<const uint8_t*>(p.Rimg.lo + rtoff);
-          const int gch0r = (nbase & 63) >> 3;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rl = i * 8 + (lane >> 2), cc = lane & 3;
-            uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
-            if (row0 + rl < p.M) {
-              const uint32_t off = ptx::sw128_offset(q * 32 + rl, (gch0r + cc) * 8);
-              vh = *reinterpret_cast<const uint4*>(rhi + off);
-              vl = *reinterpret_cast<const uint4*>(rlo + off);
-            }
-            const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
-            *reinterpret_cast<uint4*>(stgb + slot) = vh;
-            *reinterpret_cast<uint4*>(stgb + 2048 + slot) = vl;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int slot = (lane * 4 + (cc ^ ((lane >> 1) & 3))) * 16;
-            const uint4 vh = *reinterpret_cast<const uint4*>(stgb + slot);
-            const uint4 vl = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
-            const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {   // bf16 -> fp32 is a 16-bit shift
-              acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
-              acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
-            }
-          }
-          __syncwarp();
-        }
-        if (p.C) epi_store_rows_f32(p.C, p.ldc, row0, nbase, p.M, lane, stg, acc);
-        if (p.O.hi) epi_store_image(p.O, p.o_kb0, mt, nbase, q, row0, p.M, lane, stgb, acc);
-      }
+      epi_plain_tile<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN, mt, nb, q, half, lane, stg, stgb);
       ptx::tc_fence_before();
       __syncwarp();
       if (tl < 4 && warp == 2 && lane == 0) LTR_STAMP(tl * 16 + 5);
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
     }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------- chained GEMMs (one launch, several row-local layers)
+// Layers whose inputs are row-local (every output row depends only on the same row of the previous layer's
+// output) can run back to back inside ONE persistent launch: a CTA owns a 128-row m-tile and walks through
+// all n-blocks of op 0, then of op 1, ... for that m-tile.  Compared with one launch per layer this removes
+// the per-launch fill / drain / wave-quantisation bubbles (mlp1: 256 tiles and mlp2: 128 tiles on 148 SMs
+// are 2 resp. 0.86 waves; chained, 128 CTAs do 3 + 3 tiles each) - the signature layer's
+//   mlp1 (ReLU) -> mlp2 (+ residual) -> qkv of the NEXT layer (or final_proj + L2 norm)
+// chain (models/line_transformer.py:157-166,176-183,245-246) is one launch instead of three.
+// Dependency between consecutive ops of an m-tile: the producer warp waits on `op_done` until all eight
+// epilogue warps have finished (and fenced: generic-proxy global stores -> async-proxy TMA reads) the
+// previous op's tiles of this m-tile.  BN = 256 only.
+constexpr int CHAIN_MAX_OPS = 3;
+struct GemmChainArgs {
+  GemmImgArgs op[CHAIN_MAX_OPS];
+  int n_ops, m_tiles;
+};
+
+__global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constant__ GemmChainArgs c) {
+  constexpr int BN = 256;
+  using Cfg = GemmImgCfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* op_done = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&acc_full[b], 1);
+      ptx::mbar_init(&acc_empty[b], 8);
+    }
+    ptx::mbar_init(op_done, 8);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t it = 0, dep = 0;
+      for (int mt = blockIdx.x; mt < c.m_tiles; mt += gridDim.x) {
+        for (int o = 0; o < c.n_ops; ++o) {
+          const GemmImgArgs& p = c.op[o];
+          if (o > 0) {   // A of this op = output of op o-1 for this m-tile: wait until it is written and visible
+            ptx::mbar_wait(op_done, dep & 1);
+            ++dep;
+          }
+          const int nk = p.W.K / 64;
+          const uint8_t* whi = reinterpret_cast<const uint8_t*>(p.W.hi);
+          const uint8_t* wlo = reinterpret_cast<const uint8_t*>(p.W.lo);
+          for (int nb = 0; nb < p.n_blks; ++nb)
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+              const int s = it % Cfg::STAGES;
+              const uint32_t ph = (it / Cfg::STAGES) & 1;
+              ptx::mbar_wait(&empty[s], ph ^ 1);
+              uint8_t* st = smem + s * Cfg::STAGE;
+              const size_t aoff = ((size_t)mt * p.A.kblocks + p.a_kb0 + kb) * IMG_TILE_ELEMS;
+              const size_t woff = ((size_t)kb * (p.W.N / 8) + (size_t)nb * (BN / 8)) * 1024;
+              ptx::mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
+              ptx::bulk_g2s(st, p.A.hi + aoff, Cfg::A_TILE, &full[s]);
+              ptx::bulk_g2s(st + Cfg::A_TILE, p.A.lo + aoff, Cfg::A_TILE, &full[s]);
+              ptx::bulk_g2s(st + 2 * Cfg::A_TILE, whi + woff, Cfg::W_TILE, &full[s]);
+              ptx::bulk_g2s(st + 2 * Cfg::A_TILE + Cfg::W_TILE, wlo + woff, Cfg::W_TILE, &full[s]);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BN);
+      uint32_t it = 0, tl = 0;
+      for (int mt = blockIdx.x; mt < c.m_tiles; mt += gridDim.x)
+        for (int o = 0; o < c.n_ops; ++o) {
+          const int nk = c.op[o].W.K / 64, n_blks = c.op[o].n_blks;
+          for (int nb = 0; nb < n_blks; ++nb, ++tl) {
+            const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+            ptx::mbar_wait(&acc_empty[buf], aph ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * BN;
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+              const int s = it % Cfg::STAGES;
+              const uint32_t ph = (it / Cfg::STAGES) & 1;
+              ptx::mbar_wait(&full[s], ph);
+              ptx::tc_fence_after();
+              const uint32_t a_hi = ptx::smem_u32(smem + s * Cfg::STAGE);
+              const uint32_t a_lo = a_hi + Cfg::A_TILE;
+              const uint32_t w_hi = a_hi + 2 * Cfg::A_TILE;
+              const uint32_t w_lo = w_hi + Cfg::W_TILE;
+#pragma unroll
+              for (int k16 = 0; k16 < 4; ++k16) {
+                const uint32_t ko = k16 * 32;
+                const uint64_t dah = ptx::make_sw128_kmajor_desc(a_hi + ko, 1024);
+                const uint64_t dal = ptx::make_sw128_kmajor_desc(a_lo + ko, 1024);
+                const uint64_t dwh = ptx::make_sw128_kmajor_desc(w_hi + ko, 1024);
+                const uint64_t dwl = ptx::make_sw128_kmajor_desc(w_lo + ko, 1024);
+                ptx::umma_bf16(d_tmem, dal, dwh, idesc, (kb | k16) != 0);
+                ptx::umma_bf16(d_tmem, dah, dwl, idesc, 1);
+                ptx::umma_bf16(d_tmem, dah, dwh, idesc, 1);
+              }
+              ptx::umma_commit(&empty[s]);
+            }
+            ptx::umma_commit(&acc_full[buf]);
+          }
+        }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (8 warps)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (warp - 2) * Cfg::STG_WARP);
+    uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
+    uint32_t tl = 0;
+    for (int mt = blockIdx.x; mt < c.m_tiles; mt += gridDim.x)
+      for (int o = 0; o < c.n_ops; ++o) {
+        const GemmImgArgs& p = c.op[o];
+        for (int nb = 0; nb < p.n_blks; ++nb, ++tl) {
+          const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+          ptx::mbar_wait(&acc_full[buf], aph);
+          ptx::tc_fence_after();
+          const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+          if (p.norm != NORM_NONE)
+            epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
+          else
+            epi_plain_tile<BN>(p, tacc, mt, nb, q, half, lane, stg, stgb);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+        }
+        if (o + 1 < c.n_ops) {
+          // everything this warp stored for op o (generic proxy, global) must be visible to the bulk copies
+          // (async proxy) the producer issues for op o+1: device-scope fence + proxy fence, then signal
+          __threadfence();
+          ptx::fence_proxy_async_all();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(op_done);
+        }
+      }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -491,6 +661,15 @@ inline int launch_gemm_img(const GemmImgArgs& a, cudaStream_t s, int bn_hint = 0
   if (a.M <= 0) return 0;
   if (a.W.K % 64 || a.W.N % 64 || (a.C && a.ldc % 8) || (a.R && a.ldr % 4))
     return set_error(-1, "gemm_img: K%64, N%64, ldc%8, ldr%4 required");
+  {   // operand / output k-block ranges must lie inside their images (a wrong d_inner would otherwise alias tiles silently)
+    const int nblk = a.a_kb_nb ? a.W.N / 64 : 1;   // block-diagonal: 64-wide n-blocks, each with its own K slice
+    if (a.a_kb0 < 0 || a.a_kb0 + (nblk - 1) * a.a_kb_nb + a.W.K / 64 > a.A.kblocks)
+      return set_error(-1, "gemm_img: A k-block range exceeds the activation image");
+    if (a.O.hi && (a.o_kb0 < 0 || a.o_kb0 + a.W.N / 64 > a.O.kblocks))
+      return set_error(-1, "gemm_img: output columns exceed the output image");
+    if (a.Rimg.hi && (a.r_kb0 < 0 || a.r_kb0 + a.W.N / 64 > a.Rimg.kblocks))
+      return set_error(-1, "gemm_img: residual columns exceed the residual image");
+  }
   if (a.norm != NORM_NONE) {
     if (a.W.N != 256 || a.Rimg.hi || a.act != ACT_NONE || (a.nadd && a.ldadd % 4) || (a.norm == NORM_LAYER && (!a.ng || !a.nbeta)))
       return set_error(-1, "gemm_img: the row-norm epilogue needs N == 256, no activation, fp32 residual");
@@ -504,6 +683,35 @@ inline int launch_gemm_img(const GemmImgArgs& a, cudaStream_t s, int bn_hint = 0
   }
   if (bn == 256 && a.W.N % 256 == 0) return launch_gemm_img_bn<256>(a, s);
   return launch_gemm_img_bn<128>(a, s);
+}
+
+// Chain of row-local layers in one launch (see gemm_chain_kernel).  Every op: N % 256 == 0, plain A
+// (no block-diagonal slices); op i+1 must read what op i writes for the same rows only.
+inline int launch_gemm_chain(const GemmImgArgs* ops, int n_ops, cudaStream_t s) {
+  if (n_ops < 1 || n_ops > CHAIN_MAX_OPS) return set_error(-1, "gemm_chain: 1..3 ops");
+  if (ops[0].M <= 0) return 0;
+  GemmChainArgs c{};
+  c.n_ops = n_ops;
+  c.m_tiles = cdiv(ops[0].M, 128);
+  for (int i = 0; i < n_ops; ++i) {
+    GemmImgArgs a = ops[i];
+    if (a.M != ops[0].M || a.W.K % 64 || a.W.N % 256 || a.a_kb_nb || (a.C && a.ldc % 8) || (a.R && a.ldr % 4))
+      return set_error(-1, "gemm_chain: ops need equal M, K%64, N%256, no block-diagonal A");
+    if (a.a_kb0 < 0 || a.a_kb0 + a.W.K / 64 > a.A.kblocks || (a.O.hi && (a.o_kb0 < 0 || a.o_kb0 + a.W.N / 64 > a.O.kblocks)) ||
+        (a.Rimg.hi && (a.r_kb0 < 0 || a.r_kb0 + a.W.N / 64 > a.Rimg.kblocks)))
+      return set_error(-1, "gemm_chain: k-block range exceeds an image");
+    if (a.norm != NORM_NONE && (a.W.N != 256 || a.Rimg.hi || a.act != ACT_NONE))
+      return set_error(-1, "gemm_chain: the row-norm epilogue needs N == 256, no activation, fp32 residual");
+    a.m_tiles = c.m_tiles;
+    a.n_blks = a.W.N / 256;
+    c.op[i] = a;
+  }
+  using Cfg = GemmImgCfg<256>;
+  LTR_CUDA_TRY(ensure_dynamic_smem(gemm_chain_kernel, Cfg::SMEM));
+  const int grid = c.m_tiles < device_sm_count() ? c.m_tiles : device_sm_count();
+  LaunchScope ls(KC_LINEAR, s);
+  LTR_CUDA_TRY(launch_pdl(gemm_chain_kernel, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, s, c));
+  return 0;
 }
 
 // ---------------------------------------------------------------- image <-> fp32 helpers

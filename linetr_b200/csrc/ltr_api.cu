@@ -249,15 +249,32 @@ static LinearArgs lin(const float* A, int lda, const float* W, const float* b, f
 
 // One wide layer on the tensor-core engine: A image k-blocks [a_kb0, a_kb0 + K/64) -> fp32 rows C
 // (optional) and/or image O k-blocks from o_kb0 (optional); R = fp32 residual.
-static int gemm(const Lin& L, const ActImg& A, int a_kb0, int M, int act, cudaStream_t s, float* C, int ldc,
-                const ActImg* O = nullptr, int o_kb0 = 0, const float* R = nullptr, int ldr = 0,
-                const ActImg* Rimg = nullptr, int r_kb0 = 0, int bn_hint = 0, int a_kb_nb = 0) {
+static GemmImgArgs gemm_args(const Lin& L, const ActImg& A, int a_kb0, int M, int act, float* C, int ldc,
+                             const ActImg* O = nullptr, int o_kb0 = 0, const float* R = nullptr, int ldr = 0,
+                             const ActImg* Rimg = nullptr, int r_kb0 = 0, int a_kb_nb = 0) {
   GemmImgArgs a{};
   a.A = A; a.a_kb0 = a_kb0; a.W = L.tw; a.bias = L.b; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc;
   if (O) { a.O = *O; a.o_kb0 = o_kb0; }
   if (Rimg) { a.Rimg = *Rimg; a.r_kb0 = r_kb0; }
   a.M = M; a.act = act; a.a_kb_nb = a_kb_nb;
-  return launch_gemm_img(a, s, bn_hint);
+  return a;
+}
+
+static int gemm(const Lin& L, const ActImg& A, int a_kb0, int M, int act, cudaStream_t s, float* C, int ldc,
+                const ActImg* O = nullptr, int o_kb0 = 0, const float* R = nullptr, int ldr = 0,
+                const ActImg* Rimg = nullptr, int r_kb0 = 0, int bn_hint = 0, int a_kb_nb = 0) {
+  return launch_gemm_img(gemm_args(L, A, a_kb0, M, act, C, ldc, O, o_kb0, R, ldr, Rimg, r_kb0, a_kb_nb), s, bn_hint);
+}
+
+// Batches with at least this many 128-row tiles run the row-local GEMMs of a signature layer as ONE chained
+// launch (gemm_chain_kernel); smaller ones keep one launch per layer, which spreads the n-blocks of the few
+// m-tiles over more SMs.  LTR_CHAIN_MIN_TILES overrides (0 = never chain).
+static int chain_min_tiles() {
+  static const int v = [] {
+    const char* e = std::getenv("LTR_CHAIN_MIN_TILES");
+    return e ? std::atoi(e) : 96;
+  }();
+  return v;
 }
 
 // GEMM whose epilogue normalises whole rows (N = 256): LayerNorm(acc + bias (+ R)) * g + b (+ add), or
@@ -339,20 +356,32 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
     max_l = 0;
     for (int i = 0; i < in.n_images; ++i) max_l = std::max(max_l, in.cu_lines_host[i + 1] - in.cu_lines_host[i]);
   }
+  const bool chain = chain_min_tiles() > 0 && cdiv(R, 128) >= chain_min_tiles() && !out_cf && !m->sig.empty();
+  ActImg tiles{};
+  if (out_tiles) tiles = tiles_image(out_tiles, R);
+  GemmImgArgs fin = gemm_args(m->wf, w.xm, 0, R, ACT_NONE, out_rows, 256, out_tiles ? &tiles : nullptr, 0);
+  fin.norm = NORM_L2; fin.eps = 1e-6f;   // final_proj + F.normalize in one epilogue (rows-only output)
   for (size_t li = 0; li < m->sig.size(); ++li) {
     const SigLayer& L = m->sig[li];
-    LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, nullptr, 0, &w.qkv, 0));
+    if (!chain || li == 0) LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, nullptr, 0, &w.qkv, 0));
     LTR_TRY(launch_sig_attention_tc(w.qkv, w.xm, 256, cu, in.lines_per_image, max_l, in.n_images, s));  // o -> xm[:, 256:]
-    LTR_TRY(gemm(L.mlp1, w.xm, 0, R, ACT_RELU, s, nullptr, 0, &w.hm, 0));
     // x += delta: the running descriptor lives ONLY as the split-bf16 image xm[:, :256] (hi + lo carries
     // ~2^-17 relative precision; an fp32 copy would double the store traffic of this epilogue)
-    LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, nullptr, 0, &w.xm, 0, nullptr, 0, &w.xm, 0));
+    if (chain) {
+      // mlp1 -> mlp2 (+ residual, in place) -> qkv of the next layer / final projection: row-local, one launch
+      const bool last = li + 1 == m->sig.size();
+      GemmImgArgs ops[3] = {gemm_args(L.mlp1, w.xm, 0, R, ACT_RELU, nullptr, 0, &w.hm, 0),
+                            gemm_args(L.mlp2, w.hm, 0, R, ACT_NONE, nullptr, 0, &w.xm, 0, nullptr, 0, &w.xm, 0),
+                            last ? fin : gemm_args(m->sig[li + 1].qkv, w.xm, 0, R, ACT_NONE, nullptr, 0, &w.qkv, 0)};
+      LTR_TRY(launch_gemm_chain(ops, 3, s));
+    } else {
+      LTR_TRY(gemm(L.mlp1, w.xm, 0, R, ACT_RELU, s, nullptr, 0, &w.hm, 0));
+      LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, nullptr, 0, &w.xm, 0, nullptr, 0, &w.xm, 0));
+    }
   }
+  if (chain) return 0;
   if (!out_cf) {   // rows (+ matcher tile image): projection + L2 normalisation in one launch
-    ActImg tiles{};
-    if (out_tiles) tiles = tiles_image(out_tiles, R);
-    LTR_TRY(gemm_norm(m->wf, w.xm, R, s, NORM_L2, nullptr, nullptr, nullptr, 0, nullptr, 0, out_rows, 256,
-                      out_tiles ? &tiles : nullptr, 0));
+    LTR_TRY(launch_gemm_img(fin, s, 256));
     return 0;
   }
   LTR_TRY(gemm(m->wf, w.xm, 0, R, ACT_NONE, s, w.yf, 256));

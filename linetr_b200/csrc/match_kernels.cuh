@@ -120,6 +120,14 @@ __global__ void __launch_bounds__(256) segmean_kernel(SegMeanArgs p) {
   p.dist_key[(long long)pair * p.stride_key + (long long)a * K1 + b] = acc;
 }
 
+// np.argmin order on clipped distances: a NaN compares as the minimum (np.argmin returns the FIRST NaN of
+// a row; its score NaN then fails the strict `< thr`, nn_matcher.py:15-18), otherwise plain `<`.
+__device__ __forceinline__ bool nn_less(float a, int ia, float b, int ib) {
+  const bool an = a != a, bn = b != b;
+  if (an || bn) return an && (!bn || ia < ib);
+  return a < b || (a == b && ia < ib);
+}
+
 struct NNArgs {
   const float* dist; long long stride;
   const int* cuk0; const int* cuk1;  // keyline offsets per pair or nullptr (uniform)
@@ -143,14 +151,15 @@ __global__ void __launch_bounds__(256) row_argmin_kernel(NNArgs p) {
   const float* __restrict__ D = p.dist + (long long)pair * p.stride + (long long)row * K1;
   float best = INFINITY; int bi = 0x7fffffff;
   for (int j = lane; j < K1; j += 32) {
-    float v = fmaxf(D[j], 0.f);  // .clip(min=0), nn_matcher.py:12
-    if (v < best) { best = v; bi = j; }
+    float v = D[j];
+    v = v < 0.f ? 0.f : v;       // .clip(min=0), nn_matcher.py:12; a NaN stays NaN, as with np.clip
+    if (nn_less(v, j, best, bi)) { best = v; bi = j; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     float ov = __shfl_xor_sync(0xffffffffu, best, o);
     int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    if (nn_less(ov, oi, best, bi)) { best = ov; bi = oi; }
   }
   if (lane == 0) {
     p.matches0[b0 + row] = (K1 > 0) ? bi : -1;
@@ -176,8 +185,9 @@ __global__ void __launch_bounds__(256) col_argmin_kernel(NNArgs p) {
   float best = INFINITY; int bi = 0x7fffffff;
   if (col < K1) {
     for (int i = ty; i < K0; i += 8) {
-      float v = fmaxf(D[(long long)i * K1 + col], 0.f);
-      if (v < best) { best = v; bi = i; }
+      float v = D[(long long)i * K1 + col];
+      v = v < 0.f ? 0.f : v;     // NaN-preserving clip
+      if (nn_less(v, i, best, bi)) { best = v; bi = i; }
     }
   }
   sv[ty][tx] = best; si[ty][tx] = bi;
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(256) col_argmin_kernel(NNArgs p) {
 #pragma unroll
     for (int r = 1; r < 8; ++r) {
       float ov = sv[r][tx]; int oi = si[r][tx];
-      if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      if (nn_less(ov, oi, best, bi)) { best = ov; bi = oi; }
     }
     p.nn1[b1 + col] = (K0 > 0) ? bi : -1;
   }

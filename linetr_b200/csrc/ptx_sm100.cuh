@@ -51,6 +51,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// generic-proxy writes (global and shared) -> visible to async-proxy reads (TMA loads of data this CTA just stored)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ------------------------------------------------------------------ bulk async copy (TMA 1-D)
 // global -> shared, completion signalled on an mbarrier with complete_tx::bytes.
 // bytes % 16 == 0, both addresses 16-byte aligned.

@@ -36,11 +36,13 @@ struct SigAttnSmem {
 __global__ void __launch_bounds__(256) sig_attention_tc_kernel(ActImg qkv, ActImg out, int out_k0,
                                                                 const int* __restrict__ cu, int lpi) {
   using S = SigAttnSmem;
-  int lb, le;
-  image_range(cu, lpi, blockIdx.z, lb, le);
-  const int L = le - lb;
+  // Uniform batches know their line range without touching memory; for var-len batches `cu` is read
+  // only AFTER griddepcontrol.wait (nothing a preceding kernel on the stream wrote is guaranteed
+  // visible before it - several kernels of the chain can be resident ahead of their wait at once).
+  int lb = blockIdx.z * lpi, le = lb + lpi;
+  int L = lpi;
   const int q0 = blockIdx.x * 128;
-  if (q0 >= L) return;
+  if (!cu && q0 >= L) return;
   const int h = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qd = warp & 3, half = warp >> 2;
   const int row = qd * 32 + lane;   // query row of this thread (shared with its pair thread)
@@ -80,6 +82,16 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(ActImg qkv, ActIm
   uint32_t phase = 0;
   pdl_wait();   // qkv of this layer is complete; the previous reader of the output image is done
   if (tid == 0) LTR_DBG_STAMP(31);
+  if (cu) {
+    lb = cu[blockIdx.z]; le = cu[blockIdx.z + 1];
+    L = le - lb;
+    if (q0 >= L) {   // uniform per CTA: give the TMEM columns back and leave
+      ptx::tc_fence_before();
+      __syncthreads();
+      if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
+      return;
+    }
+  }
 
   // [128 rows x 64] operand tile (hi and lo plane) <- rows row0.. of this image, k-block kb of the qkv image:
   // chunk f = tid + 256 i -> row f/8, 16-byte chunk f%8 (8 lanes read one 128-byte image line)

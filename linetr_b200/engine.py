@@ -283,17 +283,17 @@ class PairEngine:
         `n_chunks` groups of pairs; the H2D copy of group i+1 runs on a side stream while group i
         is encoded and matched, so the PCIe transfer (the e2e bound: ~5.6 MB of fp32 inputs per
         pair) overlaps the kernels.  Returns (matches0 int32 [total key lines side 0], counts
-        int32 [n_pairs], offsets0) with matches0/counts still on the device."""
+        int32 [n_pairs], offsets0) with matches0/counts still on the device.  Batches with key-line
+        structure (sub_off / cuk) are cut along the same pair boundaries."""
         P = int(n_pairs)
         if host.n_images != 2 * P:
             raise ValueError("match_packed_host: batch must hold 2 * n_pairs images")
-        if host.sub_off is not None:
-            raise NotImplementedError("match_packed_host: key-line merging batches go through match_packed")
         n_chunks = max(1, min(int(n_chunks), P))
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
         cu = host.cu_lines
+        seg = host.sub_off is not None
         outs, cnts = [], []
         for c in range(n_chunks):
             p0, p1 = shard_range(P, c, n_chunks)
@@ -310,13 +310,19 @@ class PairEngine:
                 ready.record(self._copy_stream)
             main.wait_event(ready)
             cu_c = np.concatenate([cu[p0:p1 + 1] - a0, cu[P + p0 + 1:P + p1 + 1] - b0 + n0]).astype(np.int32)
-            chunk = LineBatch(*dev_t, cu_c)
+            sub_c = cuk_c = None
+            if seg:   # key lines of the chunk's images, sublines renumbered to the chunk ([side 0 | side 1])
+                ck, so = host.cuk, host.sub_off
+                k0a, k0b, k1a, k1b = int(ck[p0]), int(ck[p1]), int(ck[P + p0]), int(ck[P + p1])
+                cuk_c = np.concatenate([ck[p0:p1 + 1] - k0a, ck[P + p0 + 1:P + p1 + 1] - k1a + (k0b - k0a)]).astype(np.int32)
+                sub_c = np.concatenate([so[k0a:k0b] - a0, so[k1a:k1b + 1] - b0 + n0]).astype(np.int32)
+            chunk = LineBatch(*dev_t, cu_c, sub_c, cuk_c)
             res = self.match_packed(chunk, p1 - p0, nn_thresh, mutual)
             for d in dev_t:
                 d.record_stream(main)
             outs.append(res.matches0)
             cnts.append(res.counts)
-        return torch.cat(outs), torch.cat(cnts), cu[:P + 1]
+        return torch.cat(outs), torch.cat(cnts), (host.cuk if seg else cu)[:P + 1]
 
 
 # ------------------------------------------------------------------------------- multi-GPU

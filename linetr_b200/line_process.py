@@ -28,7 +28,7 @@ def get_dist_matrix(desc0, desc1):
     m = desc1.shape[2]
     if B == 0 or n == 0 or m == 0:
         return np.zeros((B, n, m), dtype=np.float32)
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = _ops.current_cuda_device()
     a = torch.from_numpy(desc0).to(dev, non_blocking=True)
     b = torch.from_numpy(desc1).to(dev, non_blocking=True)
     out = _ops.match_descriptors(a, b, N.LAYOUT_CHANNEL_FIRST, B, 0.0, False, n0=n, n1=m, d=d, want_matches=False)

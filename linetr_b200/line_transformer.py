@@ -170,9 +170,7 @@ class LineTransformer(nn.Module):
         desc = data["desc_sublines"]
         score = data["score_sublines"]
         data["mask_sublines"]  # read like the reference does; it cannot change the output
-        if not desc.is_cuda:
-            raise N.LtrError("linetr_b200.LineTransformer runs on CUDA only (inputs are on "
-                             f"{desc.device}); there is no CPU fallback")
+        _ops._req_cuda(desc, "desc_sublines")   # CUDA only: there is no CPU fallback
         B, L, T = int(desc.shape[0]), int(desc.shape[1]), int(desc.shape[2])
         handle = self._get_handle(desc.device)
         out_cf, _ = _ops.encode(handle, klines.reshape(B * L, 2, 2), resp.reshape(B * L, 1), angle.reshape(B * L, 2),

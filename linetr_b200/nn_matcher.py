@@ -16,9 +16,7 @@ from . import _ops
 
 
 def _device():
-    if not torch.cuda.is_available():
-        raise N.LtrError("linetr_b200 matcher needs a CUDA device (there is no CPU fallback)")
-    return torch.device("cuda", torch.cuda.current_device())
+    return _ops.current_cuda_device()
 
 
 def _dense(matches0: np.ndarray, n0: int, n1: int) -> np.ndarray:

@@ -223,3 +223,33 @@ def match_pair(sd, side0, side1, nn_thresh=0.8, image_shape=(480, 640)):
     dist = get_dist_matrix(d0, d1)[0]
     dk = subline2keyline(dist, side0["mat_klines2sublines"][0], side1["mat_klines2sublines"][0])
     return nn_matcher_distmat(dk, nn_thresh, True), dk, d0, d1
+
+
+# ---------------------------------------------------------------------------- training-side matcher
+def eval_dist(desc0, desc1):
+    """evaluations/matcher.py:22-28,66-72: ||a||^2 + ||b||^2 - 2 ab, clipped at 0; desc [d,n]."""
+    a, b = desc0.T, desc1.T
+    sq0 = np.sum(np.square(a), axis=1)[:, None]
+    sq1 = np.sum(np.square(b), axis=1)[:, None].T
+    return (sq0 + sq1 - 2.0 * (a @ b.T)).clip(min=0)
+
+
+def eval_nn_matcher_batches(desc0, desc1, nn_thresh, is_mutual_nn=False):
+    """evaluations/matcher.py:51-102: batched matcher, [b,d,n0] x [b,d,n1] -> [b,n0+1,n1+1] with a
+    dustbin row / column marking the unmatched lines of either image (and the corner set)."""
+    b, _, n0 = desc0.shape
+    n1 = desc1.shape[2]
+    out = np.zeros((b, n0 + 1, n1 + 1))
+    for i in range(b):
+        d = eval_dist(desc0[i], desc1[i])
+        idx = np.argmin(d, axis=1)
+        keep = d[np.arange(n0), idx] < nn_thresh
+        if is_mutual_nn:
+            idx2 = np.argmin(d, axis=0)
+            keep = np.logical_and(keep, np.arange(n0) == idx2[idx])
+        m1, m2 = np.arange(n0)[keep], idx[keep]
+        out[i, m1, m2] = 1
+        out[i, np.delete(np.arange(n0 + 1), m1), -1] = 1
+        out[i, -1, np.delete(np.arange(n1 + 1), m2)] = 1
+        out[i, -1, -1] = 1
+    return out

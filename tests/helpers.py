@@ -68,3 +68,63 @@ def stack(images):
 
 ENC_CASES = ["enc_L16_T21", "enc_L1_T21", "enc_L37_T5_ragged", "enc_L24_T32_ragged", "enc_L130_T21",
              "enc_L9_T21_nd2"]
+
+
+# ---------------------------------------------------------------- cfg[0] plumbing / tokenizer fixtures
+TOK_KEYS = ("klines", "length_klines", "angles", "sublines", "pnt_sublines", "mask_sublines", "resp_sublines",
+            "angle_sublines", "score_sublines", "mat_klines2sublines")
+
+
+def plumbing():
+    """Fixtures of tests/golden/make_plumbing_golden.py: the reference `Matching` run on the four bundled pairs."""
+    if "plumb" not in _cache:
+        _cache["plumb"] = dict(np.load(os.path.join(GOLDEN_DIR, "plumbing_pairs.npz")))
+        with open(os.path.join(GOLDEN_DIR, "plumbing_pairs.json")) as f:
+            _cache["plumb_meta"] = json.load(f)
+    return _cache["plumb"], _cache["plumb_meta"]
+
+
+def _rebuild_desc(mask_sublines, real, pad):
+    """desc_sublines [1,S,T,256] from the real-token descriptors and the shared pad descriptor."""
+    mask = mask_sublines[0, :, 1:, 0] > 0
+    S, T = mask.shape
+    desc = np.broadcast_to(pad.astype(np.float32), (S, T, 256)).copy()
+    desc[mask] = real
+    return desc[None]
+
+
+def plumbing_image(npz, prefix):
+    """Tokeniser dict (numpy, batch dim 1) of one captured image + the reference's line_desc."""
+    d = {k: npz[f"{prefix}_{k}"] for k in TOK_KEYS}
+    d["desc_sublines"] = _rebuild_desc(d["mask_sublines"], npz[f"{prefix}_desc_real"], npz[f"{prefix}_desc_pad"])
+    return d, npz[f"{prefix}_line_desc"]
+
+
+def tokenizer_fixture(ci):
+    if "tok" not in _cache:
+        _cache["tok"] = dict(np.load(os.path.join(GOLDEN_DIR, "tokenizer_outputs.npz")))
+    npz = _cache["tok"]
+    d = {k[len(f"c{ci}_"):]: v for k, v in npz.items() if k.startswith(f"c{ci}_") and not k.startswith(f"c{ci}_desc_")}
+    d["desc_sublines"] = _rebuild_desc(d["mask_sublines"], npz[f"c{ci}_desc_real"], npz[f"c{ci}_desc_pad"])
+    return d
+
+
+def matching_line_branch(get_dist_matrix, subline2keyline, nn_matcher_distmat, line_desc0, line_desc1, A0, A1, thr):
+    """The line branch of the reference's Matching.forward (models/matching.py:77-81), parameterised by
+    the three functions it calls, so that tests can run it over the plugin or over the oracle."""
+    distance_sublines = get_dist_matrix(line_desc0, line_desc1)[0]
+    distance_matrix = subline2keyline(distance_sublines, A0, A1)
+    match_mat = nn_matcher_distmat(distance_matrix, thr, True)
+    return match_mat, distance_matrix
+
+
+def decisive_rows(dist, thr, margin):
+    """Rows of [K0,K1] distances whose decision does not hinge on differences below `margin`."""
+    d = np.clip(np.asarray(dist, dtype=np.float64), 0.0, None)
+    K0, K1 = d.shape
+    srt = np.sort(d, axis=1)
+    row_gap = srt[:, 1] - srt[:, 0] if K1 > 1 else np.full(K0, np.inf)
+    idx = d.argmin(axis=1)
+    csrt = np.sort(d, axis=0)
+    col_gap = (csrt[1] - csrt[0]) if K0 > 1 else np.full(K1, np.inf)
+    return (row_gap > margin) & (np.abs(srt[:, 0] - thr) > margin) & (col_gap[idx] > margin)

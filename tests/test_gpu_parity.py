@@ -529,22 +529,26 @@ def test_encoder_tiles_equal_converted_tiles():
 
 @pytest.mark.parametrize("cfg", [{}, {"max_tokens": 8, "token_distance": 12}, {"min_length": 40, "max_keylines": 20}])
 def test_gpu_tokenizer_equals_cpu_glue(cfg):
-    """ltr_tokenize (GPU) vs the CPU tokenizer glue, which tests/test_tokenizer.py pins bit-exactly to
-    the reference: geometry/masks/adjacency identical, sampled descriptors to fp32 rounding."""
-    from tests.test_tokenizer import fake_lines, fake_superpoint
+    """ltr_tokenize (GPU) vs the committed outputs of the REFERENCE tokeniser (tests/golden/tokenizer_outputs.npz,
+    generated by make_plumbing_golden.py from models/line_process.py:100-196) and vs the CPU glue:
+    geometry/masks/adjacency identical, sampled descriptors to fp32 rounding."""
+    from tests.test_tokenizer import CFGS, fake_lines, fake_superpoint
     sp = fake_superpoint(7)
     sp_dev = {k: v.to(DEV) for k, v in sp.items()}
     m = LineTransformer({"mode": "train", **cfg})
     want = m.preprocess(fake_lines(7, 60), (1, 1, 480, 640), sp, None)
     got = m.preprocess(fake_lines(7, 60), (1, 1, 480, 640), sp_dev, None)
-    assert set(want.keys()) == set(got.keys())
+    ref = H.tokenizer_fixture(CFGS.index(cfg))
+    assert set(want.keys()) == set(got.keys()) == set(ref.keys())
     for k in want:
         g = got[k].cpu()
-        assert g.shape == want[k].shape, k
+        assert g.shape == want[k].shape == ref[k].shape, k
         if k == "desc_sublines":
             assert (g - want[k]).abs().max().item() < 2e-6, k
+            assert np.abs(g.numpy() - ref[k]).max() < 2e-6, k
         else:
             assert torch.equal(g, want[k]), k
+            assert np.array_equal(g.numpy(), ref[k]), k
     # and the tokenised dict drives the encoder
     out = m.eval().to(DEV)(got)["line_desc"]
     assert out.shape[1] == 256 and torch.isfinite(out).all()
@@ -582,3 +586,111 @@ def test_c_abi_error_paths():
     assert call(lpi=3) == -1                                               # LTR_E_INVALID
     with pytest.raises(N.LtrError):
         _ops.ModelHandle({"klenc.cls_token": np.zeros(256, np.float32)}, 0)   # missing checkpoint tensors
+
+
+# ------------------------------------------------------------------ cfg[0]: the reference Matching's data through the plugin
+def _shipped_model():
+    if H.shipped_weights_path() is None:
+        pytest.skip("shipped checkpoint not available")
+    if "shipped_test_mode" not in _models:
+        # exactly what models/matching.py:16 constructs from match_line_pairs.py's config (mode 'test' loads the checkpoint)
+        m = LineTransformer({"max_keylines": -1, "min_length": 16, "token_distance": 8, "nn_threshold": 0.8,
+                             "weights_path": H.shipped_weights_path()})
+        _models["shipped_test_mode"] = m.eval().to(DEV)
+    return _models["shipped_test_mode"]
+
+
+@pytest.mark.parametrize("pair", [0, 1, 2, 3])
+def test_plumbing_real_pairs_through_plugin(pair):
+    """The tokeniser dicts the UNMODIFIED reference `Matching` built for the four bundled image pairs
+    (assets/input_pairs.txt, match_line_pairs.py defaults) replayed through the plugin with the call
+    sequence of models/matching.py:41,59,77-81; outputs against what the reference produced."""
+    npz, meta = H.plumbing()
+    model = _shipped_model()
+    a, want0 = H.plumbing_image(npz, f"p{pair}_0")
+    b, want1 = H.plumbing_image(npz, f"p{pair}_1")
+    da, db = to_dev(a), to_dev(b)
+    got0 = model(da)["line_desc"].cpu().numpy()
+    got1 = model(db)["line_desc"].cpu().numpy()
+    e0, e1 = np.abs(got0 - want0).max(), np.abs(got1 - want1).max()
+    assert e0 < DESC_TOL and e1 < DESC_TOL, (e0, e1)
+    assert e0 < DESC_TOL_TIGHT and e1 < DESC_TOL_TIGHT, (e0, e1)
+    thr = model.config["nn_threshold"]
+    mat, dist = H.matching_line_branch(get_dist_matrix, model.subline2keyline, nnm.nn_matcher_distmat, got0, got1,
+                                       da["mat_klines2sublines"][0], db["mat_klines2sublines"][0], thr)
+    assert mat.dtype == np.float64 and mat.shape == (1, a["klines"].shape[1], b["klines"].shape[1])
+    assert np.abs(dist[0] - npz[f"p{pair}_scores_l"]).max() < DESC_TOL
+    got = orc.match_indices(mat)
+    want = npz[f"p{pair}_matches_l"]
+    # descriptors agree to <= 2e-4, distances to <= 1e-3: decisions the reference itself took by a smaller
+    # margin than that are not pinned by the 1e-3 contract (none differs in practice - reported below)
+    dec = H.decisive_rows(npz[f"p{pair}_scores_l"], thr, 2e-3)
+    assert np.array_equal(got[dec], want[dec])
+    assert dec.sum() >= 0.9 * len(want)
+    assert (got != want).sum() <= 1, f"{(got != want).sum()} of {len(want)} line matches differ from the reference"
+    # the batched front-end (key-line merging inside ltr_match) takes the same decisions as the drop-in call sequence
+    eng = engine.PairEngine(model, DEV)
+    res = eng.match_pairs(engine.LineBatch.from_images([a]).to(DEV), engine.LineBatch.from_images([b]).to(DEV), thr)
+    assert np.array_equal(res.pair(0).cpu().numpy(), got)
+    assert int(res.counts[0]) == int((got >= 0).sum())
+
+
+def test_plumbing_point_branch_real_superpoint_descriptors():
+    """models/matching.py:69-71: nn_matcher on the SuperPoint descriptors of a real pair (threshold 0.7)."""
+    npz, meta = H.plumbing()
+    mat, dist = nnm.nn_matcher(npz["p0_desc_pnt0"], npz["p0_desc_pnt1"], 0.7, True)
+    assert np.array_equal(orc.match_indices(mat), npz["p0_matches_p"])
+    assert int(mat.sum()) == meta["pairs"][0]["n_matches_p"]
+
+
+# ------------------------------------------------------------------ training-side matcher (evaluations/matcher.py)
+def test_eval_matcher_vs_reference_outputs():
+    """nn_matcher_batches (dustbin row/column), nn_matcher and nn_matcher_score of the
+    reference's evaluations/matcher.py, batched through ltr_match (dist_mode 1: ||a||^2 + ||b||^2 - 2ab on
+    tcgen05) - against the committed outputs of the reference functions themselves."""
+    import os
+    from linetr_b200 import eval_matcher as em
+    npz = dict(np.load(os.path.join(H.GOLDEN_DIR, "eval_matcher_outputs.npz")))
+    d0, d1 = npz["eval_desc0"], npz["eval_desc1"]
+    for mutual in (False, True):
+        got = em.nn_matcher_batches(d0, d1, 0.9, mutual)
+        assert got.dtype == np.float64 and np.array_equal(got, npz[f"eval_batches_m{int(mutual)}"])
+        one = em.nn_matcher(d0[0], d1[0], 0.9, mutual)
+        assert one.dtype == np.float32 and np.array_equal(one, npz[f"eval_single_m{int(mutual)}"])
+        assert np.array_equal(em.nn_matcher_score(npz["eval_score_in"], 0.5, mutual), npz[f"eval_score_m{int(mutual)}"])
+    assert em.nn_matcher_batches(d0[:, :, :0], d1, 0.9, True).shape == (3, 1, 132)
+
+
+def test_host_pipelined_entry_with_keyline_merging():
+    """match_packed_host on a batch whose key lines are split into sublines == match_packed on the device copy."""
+    model, sd = model_for("synthetic:0:1")
+    eng = engine.PairEngine(model, DEV)
+    rng = np.random.Generator(np.random.PCG64(8))
+    pairs = []
+    for p in range(5):
+        L = int(rng.integers(10, 50))
+        a, b, _ = syn.make_pair_inputs(1200 + p, L, 21, n_lines1=L - int(rng.integers(0, 3)))
+        for side in (a, b):
+            S = side["desc_sublines"].shape[1]
+            ns, left = [], S
+            while left > 0:
+                n = int(min(left, rng.integers(1, 4)))
+                ns.append(n)
+                left -= n
+            A = np.zeros((len(ns), S), np.float32)
+            s0 = 0
+            for i, n in enumerate(ns):
+                A[i, s0:s0 + n] = 1.0 / n
+                s0 += n
+            side["mat_klines2sublines"] = A[None]
+        pairs.append((a, b))
+    host = engine.LineBatch.from_images([a for a, _ in pairs] + [b for _, b in pairs])
+    assert host.sub_off is not None
+    want = eng.match_packed(host.to(DEV), 5, 0.8)
+    for chunks in (1, 2, 5):
+        m0, cnt, off0 = eng.match_packed_host(host.pin(), 5, 0.8, n_chunks=chunks)
+        assert torch.equal(m0, want.matches0) and torch.equal(cnt, want.counts)
+        assert np.array_equal(off0, want.offsets0)
+    for p, (a, b) in enumerate(pairs):
+        mat, _, _, _ = orc.match_pair(sd, a, b, 0.8)
+        assert np.array_equal(want.pair(p).cpu().numpy(), orc.match_indices(mat))

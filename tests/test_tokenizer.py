@@ -11,6 +11,7 @@ import torch
 from linetr_b200 import line_process as LP
 
 REF = "/root/reference"
+CFGS = [{}, {"max_tokens": 8, "token_distance": 12}, {"min_length": 40, "max_keylines": 20}]
 
 
 class FakeKeyLine:
@@ -54,8 +55,20 @@ def test_tokenizer_shapes_and_adjacency():
     assert S > K  # some key lines are longer than 21 tokens * 8 px and get split
 
 
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_cpu_tokenizer_glue_identical_to_reference_fixture(ci):
+    """Runs everywhere (no reference checkout needed): the CPU glue against the committed outputs of the
+    reference tokeniser (tests/golden/tokenizer_outputs.npz, written by make_plumbing_golden.py)."""
+    from tests import helpers as H
+    want = H.tokenizer_fixture(ci)
+    got = ours(fake_lines(7, 60), fake_superpoint(7), CFGS[ci])
+    assert set(want.keys()) == set(got.keys())
+    for k in want:
+        assert np.array_equal(got[k].numpy(), want[k]), k
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not mounted")
-@pytest.mark.parametrize("cfg", [{}, {"max_tokens": 8, "token_distance": 12}, {"min_length": 40, "max_keylines": 20}])
+@pytest.mark.parametrize("cfg", CFGS)
 def test_tokenizer_identical_to_reference(cfg):
     sys.path.insert(0, REF)
     try:
