@@ -629,6 +629,220 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ---------------------------------------------------------------- CTA-pair variant of the chained GEMM (tcgen05 cta_group::2)
+// With 128 x 256 tiles one SM has to pull 96 KB of operands (A 32 KB + W 64 KB, split-bf16) per 64-deep k-block
+// against 12 x 128 = 1536 tensor cycles: 62.5 B/cycle/SM, more than the ~43 B/cycle/SM the L2 -> SM path
+// delivers (measured: 12.7 TB/s aggregate), so the single-CTA engine tops out near 0.65 of the tensor pipe.
+// A CTA pair (cluster of 2 on one TPC) shares every W tile: each CTA loads only HALF of it (128 of the 256
+// n-rows) plus its own 128-row A tile, and one tcgen05.mma.cta_group::2 of the leader CTA multiplies
+// M = 256 (128 rows per CTA) x N = 256: 64 KB per SM per k-block = 41.7 B/cycle/SM.
+//   barriers: full (local TMA) + peer_full (peer's stage landed, relayed by the peer's otherwise idle MMA warp
+//   with a remote arrive), empty / acc_full (tcgen05.commit multicast to both CTAs), acc_empty (leader, 16
+//   arrivals: the 8 epilogue warps of each CTA), op_done (local, as in gemm_chain_kernel).
+struct GemmPairCfg {
+  static constexpr int BN = 256;
+  static constexpr int A_TILE = 16384;
+  static constexpr int W_HALF = 16384;            // one plane of this CTA's 128 x 64 half of the W tile
+  static constexpr int STAGE = 2 * A_TILE + 2 * W_HALF;
+  static constexpr int STAGES = 3;
+  static constexpr int STG_WARP = 4096;
+  static constexpr int OFF_STG = STAGES * STAGE;
+  static constexpr int OFF_BAR = OFF_STG + 8 * STG_WARP;
+  static constexpr int OFF_XCH = OFF_BAR + 256;
+  static constexpr int SMEM = OFF_XCH + 2048 + 768;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int THREADS = 320;
+};
+static_assert(GemmPairCfg::SMEM <= 232448, "gemm pair: shared memory budget");
+
+// spin with a deadline: a protocol bug must end in a trap (launch failure), not in a hung GPU box
+__device__ __forceinline__ void mbar_wait_dl(uint64_t* bar, uint32_t parity, bool cluster_scope) {
+  const long long t0 = clock64();
+  for (;;) {
+    if (cluster_scope) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(ptx::smem_u32(bar)), "r"(parity) : "memory");
+      if (ok) return;
+    } else if (ptx::mbar_try_wait(bar, parity)) {
+      return;
+    }
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {
+  using Cfg = GemmPairCfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* full = bars;                          // [3] local
+  uint64_t* peer_full = full + Cfg::STAGES;       // [3] used in the leader
+  uint64_t* empty = peer_full + Cfg::STAGES;      // [3] local, multicast commit
+  uint64_t* acc_full = empty + Cfg::STAGES;       // [2] local, multicast commit
+  uint64_t* acc_empty = acc_full + 2;             // [2] used in the leader, 16 arrivals
+  uint64_t* op_done = acc_empty + 2;              // [1] local
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_ctiles = (c.m_tiles + 1) >> 1;      // cluster tiles: pairs of 128-row m-tiles
+  const int cl0 = blockIdx.x >> 1, cl_step = gridDim.x >> 1;
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&peer_full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&acc_full[b], 1);
+      ptx::mbar_init(&acc_empty[b], 16);
+    }
+    ptx::mbar_init(op_done, 8);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();          // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer (both CTAs: own A tile, own half of W)
+    if (lane == 0) {
+      uint32_t it = 0, dep = 0;
+      for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
+        const int mt = 2 * ct + (int)rank;
+        for (int o = 0; o < c.n_ops; ++o) {
+          const GemmImgArgs& p = c.op[o];
+          if (o > 0) {
+            mbar_wait_dl(op_done, dep & 1, false);
+            ++dep;
+          }
+          const int nk = p.W.K / 64;
+          const uint8_t* whi = reinterpret_cast<const uint8_t*>(p.W.hi);
+          const uint8_t* wlo = reinterpret_cast<const uint8_t*>(p.W.lo);
+          for (int nb = 0; nb < p.n_blks; ++nb)
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+              const int s = it % Cfg::STAGES;
+              const uint32_t ph = (it / Cfg::STAGES) & 1;
+              mbar_wait_dl(&empty[s], ph ^ 1, true);
+              uint8_t* st = smem + s * Cfg::STAGE;
+              const size_t aoff = ((size_t)mt * p.A.kblocks + p.a_kb0 + kb) * IMG_TILE_ELEMS;
+              const size_t woff = ((size_t)kb * (p.W.N / 8) + (size_t)nb * (BN / 8) + (size_t)rank * 16) * 1024;
+              ptx::mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
+              ptx::bulk_g2s(st, p.A.hi + aoff, Cfg::A_TILE, &full[s]);
+              ptx::bulk_g2s(st + Cfg::A_TILE, p.A.lo + aoff, Cfg::A_TILE, &full[s]);
+              ptx::bulk_g2s(st + 2 * Cfg::A_TILE, whi + woff, Cfg::W_HALF, &full[s]);
+              ptx::bulk_g2s(st + 2 * Cfg::A_TILE + Cfg::W_HALF, wlo + woff, Cfg::W_HALF, &full[s]);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && !leader) {
+      // ---------------------------------------------------------------- peer: relay "my stage landed" to the leader
+      uint32_t it = 0;
+      for (int ct = cl0; ct < n_ctiles; ct += cl_step)
+        for (int o = 0; o < c.n_ops; ++o) {
+          const int n_st = c.op[o].n_blks * (c.op[o].W.K / 64);
+          for (int i = 0; i < n_st; ++i, ++it) {
+            const int s = it % Cfg::STAGES;
+            mbar_wait_dl(&full[s], (it / Cfg::STAGES) & 1, false);
+            ptx::mbar_arrive_cluster(ptx::mapa_shared(&peer_full[s], 0));
+          }
+        }
+    } else if (lane == 0) {
+      // ---------------------------------------------------------------- leader: MMA issuer for the pair
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(256, BN);
+      uint32_t it = 0, tl = 0;
+      for (int ct = cl0; ct < n_ctiles; ct += cl_step)
+        for (int o = 0; o < c.n_ops; ++o) {
+          const int nk = c.op[o].W.K / 64, n_blks = c.op[o].n_blks;
+          for (int nb = 0; nb < n_blks; ++nb, ++tl) {
+            const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+            mbar_wait_dl(&acc_empty[buf], aph ^ 1, true);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * BN;
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+              const int s = it % Cfg::STAGES;
+              const uint32_t ph = (it / Cfg::STAGES) & 1;
+              mbar_wait_dl(&full[s], ph, false);
+              mbar_wait_dl(&peer_full[s], ph, true);
+              ptx::tc_fence_after();
+              const uint32_t a_hi = ptx::smem_u32(smem + s * Cfg::STAGE);
+              const uint32_t a_lo = a_hi + Cfg::A_TILE;
+              const uint32_t w_hi = a_hi + 2 * Cfg::A_TILE;
+              const uint32_t w_lo = w_hi + Cfg::W_HALF;
+#pragma unroll
+              for (int k16 = 0; k16 < 4; ++k16) {
+                const uint32_t ko = k16 * 32;
+                const uint64_t dah = ptx::make_sw128_kmajor_desc(a_hi + ko, 1024);
+                const uint64_t dal = ptx::make_sw128_kmajor_desc(a_lo + ko, 1024);
+                const uint64_t dwh = ptx::make_sw128_kmajor_desc(w_hi + ko, 1024);
+                const uint64_t dwl = ptx::make_sw128_kmajor_desc(w_lo + ko, 1024);
+                ptx::umma2_bf16(d_tmem, dal, dwh, idesc, (kb | k16) != 0);
+                ptx::umma2_bf16(d_tmem, dah, dwl, idesc, 1);
+                ptx::umma2_bf16(d_tmem, dah, dwh, idesc, 1);
+              }
+              ptx::umma2_commit(&empty[s], 3);
+            }
+            ptx::umma2_commit(&acc_full[buf], 3);
+          }
+        }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (8 warps per CTA, own 128 rows)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (warp - 2) * Cfg::STG_WARP);
+    uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
+    uint32_t tl = 0;
+    for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
+      const int mt = 2 * ct + (int)rank;
+      for (int o = 0; o < c.n_ops; ++o) {
+        const GemmImgArgs& p = c.op[o];
+        for (int nb = 0; nb < p.n_blks; ++nb, ++tl) {
+          const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+          mbar_wait_dl(&acc_full[buf], aph, true);
+          ptx::tc_fence_after();
+          const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+          if (p.norm != NORM_NONE)
+            epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
+          else
+            epi_plain_tile<BN>(p, tacc, mt, nb, q, half, lane, stg, stgb);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(&acc_empty[buf]);
+            else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
+          }
+        }
+        if (o + 1 < c.n_ops) {
+          __threadfence();
+          ptx::fence_proxy_async_all();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(op_done);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();          // nobody leaves (or frees TMEM) while the peer may still signal / multiply
+  if (warp == 1) ptx::tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+}
+
 inline int device_sm_count() {
   static std::atomic<int> sms[64];   // zero-initialised; benign duplicate queries, no torn state
   int dev = 0;
@@ -687,7 +901,8 @@ inline int launch_gemm_img(const GemmImgArgs& a, cudaStream_t s, int bn_hint = 0
 
 // Chain of row-local layers in one launch (see gemm_chain_kernel).  Every op: N % 256 == 0, plain A
 // (no block-diagonal slices); op i+1 must read what op i writes for the same rows only.
-inline int launch_gemm_chain(const GemmImgArgs* ops, int n_ops, cudaStream_t s) {
+// pair = true: CTA-pair engine (gemm_chain2_kernel); the images must be padded to 256 rows (ltr_api.cu carve does).
+inline int launch_gemm_chain(const GemmImgArgs* ops, int n_ops, cudaStream_t s, bool pair = false) {
   if (n_ops < 1 || n_ops > CHAIN_MAX_OPS) return set_error(-1, "gemm_chain: 1..3 ops");
   if (ops[0].M <= 0) return 0;
   GemmChainArgs c{};
@@ -705,6 +920,14 @@ inline int launch_gemm_chain(const GemmImgArgs* ops, int n_ops, cudaStream_t s) 
     a.m_tiles = c.m_tiles;
     a.n_blks = a.W.N / 256;
     c.op[i] = a;
+  }
+  if (pair) {
+    using Cfg = GemmPairCfg;
+    LTR_CUDA_TRY(ensure_dynamic_smem(gemm_chain2_kernel, Cfg::SMEM));
+    const int clusters = std::min((c.m_tiles + 1) / 2, device_sm_count() / 2);
+    LaunchScope ls(KC_LINEAR, s);
+    LTR_CUDA_TRY(launch_pdl(gemm_chain2_kernel, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM, s, c));   // __cluster_dims__(2,1,1)
+    return 0;
   }
   using Cfg = GemmImgCfg<256>;
   LTR_CUDA_TRY(ensure_dynamic_smem(gemm_chain_kernel, Cfg::SMEM));

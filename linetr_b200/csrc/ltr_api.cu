@@ -276,6 +276,14 @@ static int chain_min_tiles() {
   }();
   return v;
 }
+// LTR_GEMM_PAIR=0 runs the chains on the single-CTA engine instead of the CTA-pair (cta_group::2) one.
+static bool gemm_pair() {
+  static const bool v = [] {
+    const char* e = std::getenv("LTR_GEMM_PAIR");
+    return e ? std::atoi(e) != 0 : true;
+  }();
+  return v;
+}
 
 // GEMM whose epilogue normalises whole rows (N = 256): LayerNorm(acc + bias (+ R)) * g + b (+ add), or
 // the L2 normalisation of the final projection (g == nullptr): one launch instead of a GEMM, a
@@ -373,7 +381,7 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
       GemmImgArgs ops[3] = {gemm_args(L.mlp1, w.xm, 0, R, ACT_RELU, nullptr, 0, &w.hm, 0),
                             gemm_args(L.mlp2, w.hm, 0, R, ACT_NONE, nullptr, 0, &w.xm, 0, nullptr, 0, &w.xm, 0),
                             last ? fin : gemm_args(m->sig[li + 1].qkv, w.xm, 0, R, ACT_NONE, nullptr, 0, &w.qkv, 0)};
-      LTR_TRY(launch_gemm_chain(ops, 3, s));
+      LTR_TRY(launch_gemm_chain(ops, 3, s, gemm_pair()));
     } else {
       LTR_TRY(gemm(L.mlp1, w.xm, 0, R, ACT_RELU, s, nullptr, 0, &w.hm, 0));
       LTR_TRY(gemm(L.mlp2, w.hm, 0, R, ACT_NONE, s, nullptr, 0, &w.xm, 0, nullptr, 0, &w.xm, 0));
@@ -763,7 +771,7 @@ static int run_match_tc(const LtrMatchInput& in, const LtrMatchOutput& out, cons
     ta.matches0 = out.matches0; ta.scores0 = out.scores0; ta.nn1 = out.nn1; ta.counts = out.counts;
     ta.max0 = pl.mx[0];
     LaunchScope ls(KC_MATCH_TAIL, s);
-    LTR_CUDA_TRY(launch_pdl(match_tail_kernel, dim3(cdiv(pl.mx[0] + (in.mutual ? pl.mx[1] : 0), 8), P), dim3(256), 0, s, ta));
+    LTR_CUDA_TRY(launch_pdl(match_tail_kernel, dim3(cdiv(pl.mx[0] + (in.mutual ? pl.mx[1] : 0), 256), P), dim3(256), 0, s, ta));
   }
   return 0;
 }

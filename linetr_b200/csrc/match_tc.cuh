@@ -422,59 +422,101 @@ __device__ __forceinline__ void exact_row(const MatchTailArgs& p, int sa, int pa
   __syncwarp();
 }
 
-// grid = (ceil((max0 + max1) / 8), n_pairs), 256 threads = 8 warps, one line per warp: warps below max0
-// decide side-0 lines (matches0 / scores0 / counts), the others publish nn1 (argmin over axis 0).
+// One decision (warp-cooperative; used for the lines whose slots are flagged ambiguous): side-0 line i ->
+// matches0 / scores0 (returns keep), or side-1 line j -> nn1.
+__device__ __forceinline__ bool tail_decide_row(const MatchTailArgs& p, int i, int b0, int n0, int b1, int n1, float* xrow, int lane,
+                                                bool force_exact) {
+  const uint2 s = p.slot[0][b0 + i];
+  float v = __uint_as_float(s.x);
+  int idx = (int)(s.y & 0x7fffffffu);
+  if (force_exact || (s.y >> 31) || !(fabsf(v - p.thr) >= MATCH_EPS)) exact_row(p, 0, b0, n0, i, b1, n1, xrow, lane, v, idx);
+  bool keep = v < p.thr;   // strict '<' (nn_matcher.py:18)
+  if (keep && p.mutual) {
+    const uint2 t = p.slot[1][b1 + idx];
+    int back = (int)(t.y & 0x7fffffffu);
+    if (t.y >> 31) {
+      float bv;
+      exact_row(p, 1, b1, n1, idx, b0, n0, xrow, lane, bv, back);
+    }
+    keep = back == i;
+  }
+  if (lane == 0) {
+    p.matches0[b0 + i] = keep ? idx : -1;
+    p.scores0[b0 + i] = v;
+  }
+  return keep;
+}
+
+// grid = (ceil((max0 + max1) / 256), n_pairs), 256 threads, one line per THREAD on the fast path: items below
+// max0 decide side-0 lines (matches0 / scores0 / counts), the others publish nn1 (argmin over axis 0).
+// Lines whose tensor-core result cannot be trusted (ambiguous slot, score next to the threshold, or an
+// ambiguous partner column) go to a shared work list that the block's 8 warps then process
+// cooperatively with exact fp32 arithmetic.
 __global__ void __launch_bounds__(256) match_tail_kernel(MatchTailArgs p) {
   __shared__ float xrows[8][MT_D];
+  __shared__ int work[256];
+  __shared__ int n_work, n_keep;
   pdl_launch_dependents();
   pdl_wait();
-  const int pair = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int b0, e0, b1, e1;
   image_range(p.cu[0], p.n[0], pair, b0, e0);
   image_range(p.cu[1], p.n[1], pair, b1, e1);
   const int n0 = e0 - b0, n1 = e1 - b1;
-  int w = blockIdx.x * 8 + warp;
+  if (tid == 0) { n_work = 0; n_keep = 0; }
+  __syncthreads();
+  const int w = blockIdx.x * 256 + tid;
+  bool keep = false;
   if (w < p.max0) {
     const int i = w;
-    if (i >= n0) return;
-    if (n1 == 0) {
-      if (lane == 0) { p.matches0[b0 + i] = -1; p.scores0[b0 + i] = INFINITY; }
-      return;
-    }
-    const uint2 s = p.slot[0][b0 + i];
-    float v = __uint_as_float(s.x);
-    int idx = (int)(s.y & 0x7fffffffu);
-    if ((s.y >> 31) || !(fabsf(v - p.thr) >= MATCH_EPS)) exact_row(p, 0, b0, n0, i, b1, n1, xrows[warp], lane, v, idx);
-    bool keep = v < p.thr;   // strict '<' (nn_matcher.py:18)
-    if (keep && p.mutual) {
-      const uint2 t = p.slot[1][b1 + idx];
-      int back = (int)(t.y & 0x7fffffffu);
-      if (t.y >> 31) {
-        float bv;
-        exact_row(p, 1, b1, n1, idx, b0, n0, xrows[warp], lane, bv, back);
+    if (i < n0) {
+      if (n1 == 0) {
+        p.matches0[b0 + i] = -1;
+        p.scores0[b0 + i] = INFINITY;
+      } else {
+        const uint2 s = p.slot[0][b0 + i];
+        const float v = __uint_as_float(s.x);
+        const int idx = (int)(s.y & 0x7fffffffu);
+        bool hard = (s.y >> 31) || !(fabsf(v - p.thr) >= MATCH_EPS);
+        if (!hard) {
+          keep = v < p.thr;
+          if (keep && p.mutual) {
+            const uint2 t = p.slot[1][b1 + idx];
+            if (t.y >> 31) { hard = true; keep = false; }
+            else keep = (int)(t.y & 0x7fffffffu) == i;
+          }
+        }
+        if (hard) work[atomicAdd(&n_work, 1)] = w;
+        else { p.matches0[b0 + i] = keep ? idx : -1; p.scores0[b0 + i] = v; }
       }
-      keep = back == i;
     }
-    if (lane == 0) {
-      p.matches0[b0 + i] = keep ? idx : -1;
-      p.scores0[b0 + i] = v;
-      if (keep) atomicAdd(&p.counts[pair], 1);
-    }
-  } else {
+  } else if (p.mutual) {
     const int j = w - p.max0;
-    if (j >= n1 || !p.mutual) return;
-    if (n0 == 0) {
-      if (lane == 0) p.nn1[b1 + j] = -1;
-      return;
+    if (j < n1) {
+      if (n0 == 0) p.nn1[b1 + j] = -1;
+      else {
+        const uint2 t = p.slot[1][b1 + j];
+        if (t.y >> 31) work[atomicAdd(&n_work, 1)] = w;
+        else p.nn1[b1 + j] = (int)(t.y & 0x7fffffffu);
+      }
     }
-    const uint2 t = p.slot[1][b1 + j];
-    int back = (int)(t.y & 0x7fffffffu);
-    if (t.y >> 31) {
-      float bv;
-      exact_row(p, 1, b1, n1, j, b0, n0, xrows[warp], lane, bv, back);
-    }
-    if (lane == 0) p.nn1[b1 + j] = back;
   }
+  const unsigned kb = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0 && kb) atomicAdd(&n_keep, __popc(kb));
+  __syncthreads();
+  for (int e = warp; e < n_work; e += 8) {     // exact path, one work item per warp at a time
+    const int ww = work[e];
+    if (ww < p.max0) {
+      if (tail_decide_row(p, ww, b0, n0, b1, n1, xrows[warp], lane, false) && lane == 0) atomicAdd(&n_keep, 1);
+    } else {
+      const int j = ww - p.max0;
+      float bv; int back;
+      exact_row(p, 1, b1, n1, j, b0, n0, xrows[warp], lane, bv, back);
+      if (lane == 0) p.nn1[b1 + j] = back;
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && n_keep) atomicAdd(&p.counts[pair], n_keep);
 }
 
 }  // namespace ltr
