@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(320, 1) gemm_img_kernel(GemmImgArgs p) {
 // Dependency between consecutive ops of an m-tile: the producer warp waits on `op_done` until all eight
 // epilogue warps have finished (and fenced: generic-proxy global stores -> async-proxy TMA reads) the
 // previous op's tiles of this m-tile.  BN = 256 only.
-constexpr int CHAIN_MAX_OPS = 3;
+constexpr int CHAIN_MAX_OPS = 4;
 struct GemmChainArgs {
   GemmImgArgs op[CHAIN_MAX_OPS];
   int n_ops, m_tiles;
@@ -903,7 +903,7 @@ inline int launch_gemm_img(const GemmImgArgs& a, cudaStream_t s, int bn_hint = 0
 // (no block-diagonal slices); op i+1 must read what op i writes for the same rows only.
 // pair = true: CTA-pair engine (gemm_chain2_kernel); the images must be padded to 256 rows (ltr_api.cu carve does).
 inline int launch_gemm_chain(const GemmImgArgs* ops, int n_ops, cudaStream_t s, bool pair = false) {
-  if (n_ops < 1 || n_ops > CHAIN_MAX_OPS) return set_error(-1, "gemm_chain: 1..3 ops");
+  if (n_ops < 1 || n_ops > CHAIN_MAX_OPS) return set_error(-1, "gemm_chain: 1..4 ops");
   if (ops[0].M <= 0) return 0;
   GemmChainArgs c{};
   c.n_ops = n_ops;

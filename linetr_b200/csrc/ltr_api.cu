@@ -285,19 +285,6 @@ static bool gemm_pair() {
   return v;
 }
 
-// GEMM whose epilogue normalises whole rows (N = 256): LayerNorm(acc + bias (+ R)) * g + b (+ add), or
-// the L2 normalisation of the final projection (g == nullptr): one launch instead of a GEMM, a
-// normalisation kernel and the fp32 round trip between them.
-static int gemm_norm(const Lin& L, const ActImg& A, int M, cudaStream_t s, int norm, const float* g, const float* beta,
-                     const float* R, int ldr, const float* add, int ldadd, float* C, int ldc, const ActImg* O, int o_kb0) {
-  GemmImgArgs a{};
-  a.A = A; a.W = L.tw; a.bias = L.b; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc;
-  if (O) { a.O = *O; a.o_kb0 = o_kb0; }
-  a.M = M; a.act = ACT_NONE;
-  a.norm = norm; a.eps = 1e-6f; a.ng = g; a.nbeta = beta; a.nadd = add; a.ldadd = ldadd;
-  return launch_gemm_img(a, s, 256);
-}
-
 template <bool TOKEN>
 static int launch_small_mlp(const SmallMlpWeights& w, const float* in0, const float* in1, const float* in2, ActImg out,
                             int rows, float width, float height, cudaStream_t s) {
@@ -349,29 +336,43 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   }
   // ---- line stage: V projection (block diagonal over heads), fc + CLS residual, LN, FFN, LN, + line pos ----
   LTR_TRY(gemm(m->wv, w.z, 0, R, ACT_NONE, s, nullptr, 0, &w.ctx, 0, nullptr, 0, nullptr, 0, 64, 4));
-  // fc (+ CLS residual folded into the bias) -> LayerNorm in the epilogue -> y1 (fp32 rows for the FFN residual + image)
-  LTR_TRY(gemm_norm(m->wfc, w.ctx, R, s, NORM_LAYER, m->ln1g, m->ln1b, nullptr, 0, nullptr, 0, w.y1, 256, &w.y1i, 0));
-  LTR_TRY(gemm(m->w1, w.y1i, 0, R, ACT_GELU, s, nullptr, 0, &w.g, 0));
+  const bool chain = chain_min_tiles() > 0 && cdiv(R, 128) >= chain_min_tiles() && !out_cf && !m->sig.empty();
+  const bool chain_line = chain && m->cfg.d_inner % 256 == 0;
+  // line positional encoder first (its output is added in the w_2 epilogue)
   LTR_TRY(launch_small_mlp<false>(m->lpe.head, in.sublines, in.resp, in.angle, w.l128, R, in.image_width,
                                   in.image_height, s));
   LTR_TRY(gemm(m->lpe.l4, w.l128, 0, R, ACT_RELU, s, nullptr, 0, &w.l256, 0));
   LTR_TRY(gemm(m->lpe.l5, w.l256, 0, R, ACT_NONE, s, w.lpos, 256));
-  // sentence = klines_pos + LN(y1 + ffn)  -> image xm[:, :256] (the running descriptor), all in the w_2 epilogue
-  LTR_TRY(gemm_norm(m->w2, w.g, R, s, NORM_LAYER, m->ln2g, m->ln2b, w.y1, 256, w.lpos, 256, nullptr, 0, &w.xm, 0));
+  {
+    // fc (+ CLS residual folded into the bias) -> LayerNorm in the epilogue -> y1 (fp32 rows for the FFN residual + image)
+    GemmImgArgs fc = gemm_args(m->wfc, w.ctx, 0, R, ACT_NONE, w.y1, 256, &w.y1i, 0);
+    fc.norm = NORM_LAYER; fc.eps = 1e-6f; fc.ng = m->ln1g; fc.nbeta = m->ln1b;
+    GemmImgArgs w1 = gemm_args(m->w1, w.y1i, 0, R, ACT_GELU, nullptr, 0, &w.g, 0);
+    // sentence = klines_pos + LN(y1 + ffn)  -> image xm[:, :256] (the running descriptor), all in the w_2 epilogue
+    GemmImgArgs w2 = gemm_args(m->w2, w.g, 0, R, ACT_NONE, nullptr, 0, &w.xm, 0, w.y1, 256);
+    w2.norm = NORM_LAYER; w2.eps = 1e-6f; w2.ng = m->ln2g; w2.nbeta = m->ln2b; w2.nadd = w.lpos; w2.ldadd = 256;
+    if (chain_line) {   // row-local: fc -> w_1 -> w_2 -> qkv of signature layer 0 in one launch
+      GemmImgArgs ops[4] = {fc, w1, w2, gemm_args(m->sig[0].qkv, w.xm, 0, R, ACT_NONE, nullptr, 0, &w.qkv, 0)};
+      LTR_TRY(launch_gemm_chain(ops, 4, s, gemm_pair()));
+    } else {
+      LTR_TRY(launch_gemm_img(fc, s, 256));
+      LTR_TRY(launch_gemm_img(w1, s));
+      LTR_TRY(launch_gemm_img(w2, s, 256));
+    }
+  }
   // ---- line signature layers ----
   int max_l = in.lines_per_image;
   if (in.cu_lines_host) {
     max_l = 0;
     for (int i = 0; i < in.n_images; ++i) max_l = std::max(max_l, in.cu_lines_host[i + 1] - in.cu_lines_host[i]);
   }
-  const bool chain = chain_min_tiles() > 0 && cdiv(R, 128) >= chain_min_tiles() && !out_cf && !m->sig.empty();
   ActImg tiles{};
   if (out_tiles) tiles = tiles_image(out_tiles, R);
   GemmImgArgs fin = gemm_args(m->wf, w.xm, 0, R, ACT_NONE, out_rows, 256, out_tiles ? &tiles : nullptr, 0);
   fin.norm = NORM_L2; fin.eps = 1e-6f;   // final_proj + F.normalize in one epilogue (rows-only output)
   for (size_t li = 0; li < m->sig.size(); ++li) {
     const SigLayer& L = m->sig[li];
-    if (!chain || li == 0) LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, nullptr, 0, &w.qkv, 0));
+    if (!chain || (li == 0 && !chain_line)) LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, nullptr, 0, &w.qkv, 0));
     LTR_TRY(launch_sig_attention_tc(w.qkv, w.xm, 256, cu, in.lines_per_image, max_l, in.n_images, s));  // o -> xm[:, 256:]
     // x += delta: the running descriptor lives ONLY as the split-bf16 image xm[:, :256] (hi + lo carries
     // ~2^-17 relative precision; an fp32 copy would double the store traffic of this epilogue)
