@@ -323,7 +323,7 @@ def main():
     import torch
     import torch.distributed as dist
     from linetr_b200 import LineBatch, LineTransformer, PairEngine, _native, _ops
-    from linetr_b200.engine import gather_counts
+    from linetr_b200.engine import PeerCounts, gather_counts
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -361,20 +361,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The path's one collective (every rank learns all per-pair match counts).  Default: fused into the matcher's
+    # tail kernel - its last block stores the counts into every rank's symmetric buffer over NVLink (multimem.st
+    # / peer stores), no NCCL kernel competes with the persistent CTAs for an SM slot.  LTR_BENCH_GATHER=nccl:
+    # ncclAllGather on NCCL's stream (the round-1 path).
+    gather_mode = os.environ.get("LTR_BENCH_GATHER", "p2p") if world > 1 else "none"
+    peer = None
+    if gather_mode == "p2p":
+        try:
+            peer = PeerCounts(P)
+            gather_mode = "p2p-multimem" if peer.multicast else "p2p-stores"
+        except Exception as e:   # symmetric memory unavailable: say so and use NCCL
+            gather_mode = f"nccl (PeerCounts unavailable: {type(e).__name__})"
+    config["count_gather"] = gather_mode
     pending = []   # all-gathers in flight: the gather of step i overlaps the kernels of step i+1
+    gathered = {}
 
     def drain():
         while pending:
             pending.pop(0)[1].wait()
+        while peer is not None and peer._collected < peer._published:
+            gathered["last"] = peer.collect()
 
-    def run_resident():
+    def run_resident(gather=None):
         if wl == "cfg4":
-            out = _ops.match_descriptors(res0, res1, _native.LAYOUT_ROWS, P, 0.8, True, n0=1024, n1=1024, want_dist=False)
+            out = _ops.match_descriptors(res0, res1, _native.LAYOUT_ROWS, P, 0.8, True, n0=1024, n1=1024, want_dist=False,
+                                         gather=gather)
             return out["matches0"], out["counts"]
-        res = eng.match_packed(resident, P, 0.8)
+        res = eng.match_packed(resident, P, 0.8, gather=gather)
         return res.matches0, res.counts
 
     def step_resident():
+        if peer is not None:
+            m0, cnt = run_resident(peer.publish())
+            if peer._published - peer._collected >= 2:    # collect step i-1 behind step i: never waits in practice
+                gathered["last"] = peer.collect()
+            return m0, cnt
         m0, cnt = run_resident()
         if world > 1:
             drain()

@@ -160,6 +160,30 @@ typedef struct {
   int32_t tiles_row0_0, tiles_row0_1;
 } LtrMatchInput;
 
+/* Multi-GPU: the path's ONE collective - every rank learns the per-pair match counts of all ranks - fused
+ * into the matcher's tail kernel.  The caller owns a SYMMETRIC int32 buffer (same size on every rank, peer
+ * mapped over NVLink, e.g. torch.distributed._symmetric_memory) laid out as
+ *     counts[LTR_GATHER_SLOTS][world][n_pairs]  followed by  flags[LTR_GATHER_SLOTS][world].
+ * The last thread block of the tail kernel stores this rank's n_pairs counts into row `rank` of slot `slot`
+ * of EVERY rank's buffer - one multimem.st per element through the NVSwitch multicast address when `mc_base`
+ * is given, else plain stores through the `world` peer pointers - and then publishes flags[slot][rank] =
+ * epoch the same way.  No NCCL kernel, no extra launch on the producing side; ltr_gather_wait (one tiny
+ * block) waits for the `world` flags of a slot and copies the gathered counts out.  A rank may run at most
+ * LTR_GATHER_SLOTS - 2 steps ahead of its own ltr_gather_wait calls. */
+#define LTR_GATHER_SLOTS 4
+typedef struct {
+  void* mc_base;               /* multicast address of the symmetric buffer or NULL */
+  void* const* peer_bases;     /* device array [world]: address of the buffer on every rank (used if !mc_base) */
+  int32_t rank, world;
+  int32_t slot;                /* 0 .. LTR_GATHER_SLOTS-1 */
+  int32_t epoch;               /* > 0, increasing per use of a slot */
+} LtrPeerGather;
+
+/* Waits (on the stream) until flags[slot][0..world) of the LOCAL symmetric buffer have all reached `epoch`, then
+ * copies counts[slot] (world * n_pairs int32) to `out`. */
+int ltr_gather_wait(const void* local_base, int32_t world, int32_t n_pairs, int32_t slot, int32_t epoch,
+                    int32_t* out, int32_t device, void* stream);
+
 /* Outputs (device).  Keyline k of side 0 lives at index cuk0[p]+k (cu0[p]+k without
  * merging, p*n0+k for a uniform batch); likewise side 1.
  * matches0[k] = index (local to the pair) of the matched keyline in side 1, or -1;
@@ -183,6 +207,7 @@ typedef struct {
   float* dist_sub;
   void* workspace;
   int64_t workspace_bytes;
+  const LtrPeerGather* gather;   /* optional (d == 256, no merging): publish `counts` to all ranks, see above */
 } LtrMatchOutput;
 
 int64_t ltr_match_workspace_bytes(const LtrMatchInput* in);

@@ -21,7 +21,7 @@ LAYOUT_CHANNEL_FIRST = 1
 # Every symbol include/linetr_b200.h declares (tests check the library exports all of them).
 EXPORTED_SYMBOLS = (
     "ltr_abi_version", "ltr_last_error", "ltr_create", "ltr_destroy", "ltr_encode_workspace_bytes",
-    "ltr_desc_tiles_bytes", "ltr_encode", "ltr_match_workspace_bytes", "ltr_match", "ltr_match_distmat",
+    "ltr_desc_tiles_bytes", "ltr_encode", "ltr_match_workspace_bytes", "ltr_match", "ltr_gather_wait", "ltr_match_distmat",
     "ltr_merge_sublines", "ltr_tokenize", "ltr_linear", "ltr_linear_img", "ltr_linear_img_norm",
     "ltr_launch_count", "ltr_reset_launch_count", "ltr_profile_begin", "ltr_profile_end",
 )
@@ -67,10 +67,18 @@ class LtrMatchInput(C.Structure):
                 ("tiles_row0_0", C.c_int32), ("tiles_row0_1", C.c_int32)]
 
 
+GATHER_SLOTS = 4
+
+
+class LtrPeerGather(C.Structure):
+    _fields_ = [("mc_base", C.c_void_p), ("peer_bases", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32),
+                ("slot", C.c_int32), ("epoch", C.c_int32)]
+
+
 class LtrMatchOutput(C.Structure):
     _fields_ = [("matches0", C.c_void_p), ("scores0", C.c_void_p), ("nn1", C.c_void_p),
                 ("counts", C.c_void_p), ("dist_key", C.c_void_p), ("dist_sub", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("gather", C.POINTER(LtrPeerGather))]
 
 
 class LtrTokenizeInput(C.Structure):
@@ -114,6 +122,8 @@ def load():
     lib.ltr_match_workspace_bytes.restype = C.c_int64
     lib.ltr_match.argtypes = [C.POINTER(LtrMatchInput), C.POINTER(LtrMatchOutput), C.c_int32, C.c_void_p]
     lib.ltr_match.restype = C.c_int
+    lib.ltr_gather_wait.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.ltr_gather_wait.restype = C.c_int
     lib.ltr_match_distmat.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_float,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_void_p]

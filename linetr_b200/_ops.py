@@ -163,13 +163,14 @@ def _match_workspace(dev, need: int) -> torch.Tensor:
 def match_descriptors(desc0, desc1, layout, n_pairs, nn_thresh, mutual=True, *, n0=0, n1=0, cu0=None, cu1=None,
                       max_n0=0, max_n1=0, sub_off0=None, sub_off1=None, cuk0=None, cuk1=None, max_k0=0, max_k1=0,
                       total_k0=None, total_k1=None, d=256, want_dist=True, want_matches=True, dist_mode=0,
-                      tiles0=None, tiles1=None, tiles_lines=(0, 0), tiles_row0=(0, 0)):
+                      tiles0=None, tiles1=None, tiles_lines=(0, 0), tiles_row0=(0, 0), gather=None):
     """ltr_match.  Returns dict(matches0, scores0, nn1, counts, dist_key, stride).
 
     want_dist=False (no key-line merging, d == 256) never materialises the distance matrix: the row
     argmin lives in the epilogue of the tensor-core contraction.  want_matches=False computes the
     distance matrices only (get_dist_matrix).  tiles0/tiles1: descriptor tile images from
-    `encode(want_tiles=True)` (uniform batches with n % 128 == 0)."""
+    `encode(want_tiles=True)` (uniform batches with n % 128 == 0).  gather: an `N.LtrPeerGather` - the tail
+    kernel then also publishes the per-pair counts to every rank (engine.PeerCounts)."""
     _req_cuda(desc0, "desc0")
     _req_cuda(desc1, "desc1")
     dev = desc0.device
@@ -214,7 +215,8 @@ def match_descriptors(desc0, desc1, layout, n_pairs, nn_thresh, mutual=True, *, 
     ws = _match_workspace(dev, need)
     g = lambda k: out[k].data_ptr() if out.get(k) is not None else None
     o = N.LtrMatchOutput(g("matches0"), g("scores0"), g("nn1"), g("counts"), g("dist_key"),
-                         dist_sub.data_ptr() if dist_sub is not None else None, ws.data_ptr(), ws.numel())
+                         dist_sub.data_ptr() if dist_sub is not None else None, ws.data_ptr(), ws.numel(),
+                         C.pointer(gather) if gather is not None else None)
     with torch.cuda.device(dev):
         rc = lib.ltr_match(C.byref(inp), C.byref(o), dev.index, _stream_ptr(dev))
     N.check(rc, "ltr_match")

@@ -520,6 +520,7 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
+  if (tid == 0) LTR_DBG_STAMP(110);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -531,6 +532,7 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
           if (o > 0) {   // A of this op = output of op o-1 for this m-tile: wait until it is written and visible
             ptx::mbar_wait(op_done, dep & 1);
             ++dep;
+            if (dep < 8) LTR_DBG_STAMP(100 + dep);
           }
           const int nk = p.W.K / 64;
           const uint8_t* whi = reinterpret_cast<const uint8_t*>(p.W.hi);
@@ -564,12 +566,14 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
             const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
             ptx::mbar_wait(&acc_empty[buf], aph ^ 1);
             ptx::tc_fence_after();
+            if (tl < 10) LTR_DBG_STAMP(40 + tl * 4);
             const uint32_t d_tmem = tmem_base + buf * BN;
             for (int kb = 0; kb < nk; ++kb, ++it) {
               const int s = it % Cfg::STAGES;
               const uint32_t ph = (it / Cfg::STAGES) & 1;
               ptx::mbar_wait(&full[s], ph);
               ptx::tc_fence_after();
+              if (tl < 10 && kb == 0) LTR_DBG_STAMP(41 + tl * 4);
               const uint32_t a_hi = ptx::smem_u32(smem + s * Cfg::STAGE);
               const uint32_t a_lo = a_hi + Cfg::A_TILE;
               const uint32_t w_hi = a_hi + 2 * Cfg::A_TILE;
@@ -588,6 +592,7 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
               ptx::umma_commit(&empty[s]);
             }
             ptx::umma_commit(&acc_full[buf]);
+            if (tl < 10) LTR_DBG_STAMP(42 + tl * 4);
           }
         }
     }
@@ -606,12 +611,14 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
           ptx::mbar_wait(&acc_full[buf], aph);
           ptx::tc_fence_after();
           const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+          if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(80 + tl);
           if (p.norm != NORM_NONE)
             epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
           else
             epi_plain_tile<BN>(p, tacc, mt, nb, q, half, lane, stg, stgb);
           ptx::tc_fence_before();
           __syncwarp();
+          if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(43 + tl * 4);
           if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
         }
         if (o + 1 < c.n_ops) {
@@ -716,6 +723,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
+  if (tid == 0) LTR_DBG_STAMP(110);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs: own A tile, own half of W)
@@ -728,6 +736,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
           if (o > 0) {
             mbar_wait_dl(op_done, dep & 1, false);
             ++dep;
+            if (dep < 8) LTR_DBG_STAMP(100 + dep);
           }
           const int nk = p.W.K / 64;
           const uint8_t* whi = reinterpret_cast<const uint8_t*>(p.W.hi);
@@ -773,6 +782,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
             const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
             mbar_wait_dl(&acc_empty[buf], aph ^ 1, true);
             ptx::tc_fence_after();
+            if (tl < 10) LTR_DBG_STAMP(40 + tl * 4);
             const uint32_t d_tmem = tmem_base + buf * BN;
             for (int kb = 0; kb < nk; ++kb, ++it) {
               const int s = it % Cfg::STAGES;
@@ -780,6 +790,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
               mbar_wait_dl(&full[s], ph, false);
               mbar_wait_dl(&peer_full[s], ph, true);
               ptx::tc_fence_after();
+              if (tl < 10 && kb == 0) LTR_DBG_STAMP(41 + tl * 4);
               const uint32_t a_hi = ptx::smem_u32(smem + s * Cfg::STAGE);
               const uint32_t a_lo = a_hi + Cfg::A_TILE;
               const uint32_t w_hi = a_hi + 2 * Cfg::A_TILE;
@@ -798,6 +809,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
               ptx::umma2_commit(&empty[s], 3);
             }
             ptx::umma2_commit(&acc_full[buf], 3);
+            if (tl < 10) LTR_DBG_STAMP(42 + tl * 4);
           }
         }
     }
@@ -817,12 +829,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
           mbar_wait_dl(&acc_full[buf], aph, true);
           ptx::tc_fence_after();
           const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+          if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(80 + tl);
           if (p.norm != NORM_NONE)
             epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
           else
             epi_plain_tile<BN>(p, tacc, mt, nb, q, half, lane, stg, stgb);
           ptx::tc_fence_before();
           __syncwarp();
+          if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(43 + tl * 4);
           if (lane == 0) {
             if (leader) ptx::mbar_arrive(&acc_empty[buf]);
             else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));

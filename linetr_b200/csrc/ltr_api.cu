@@ -665,6 +665,7 @@ struct MatchPlan {
   ActImg img[2];
   uint2* slot[2];
   float* sq[2];
+  int* done;
   int64_t bytes;
 };
 
@@ -701,6 +702,7 @@ static MatchPlan plan_match(const LtrMatchInput& in, char* base) {
     pl.slot[s] = reinterpret_cast<uint2*>(take((int64_t)std::max(pl.total[s], 1) * 8));
     pl.sq[s] = in.dist_mode == 1 ? reinterpret_cast<float*>(take((int64_t)std::max(pl.total[s], 1) * 4)) : nullptr;
   }
+  pl.done = reinterpret_cast<int*>(take(256));
   pl.bytes = off;
   return pl;
 }
@@ -755,12 +757,14 @@ static int run_match_tc(const LtrMatchInput& in, const LtrMatchOutput& out, cons
     ma.dist = seg ? out.dist_sub : out.dist_key;
     ma.dist_stride = seg ? (long long)pl.mx[0] * pl.mx[1] : stride_key;
     ma.counts = want_nn ? out.counts : nullptr;
+    ma.done = want_nn ? pl.done : nullptr;
     ma.n_pairs = P;
     LTR_CUDA_TRY(ensure_dynamic_smem(match_tc_kernel, MT_SMEM));
     LaunchScope ls(KC_MATCH_TC, s);
     LTR_CUDA_TRY(launch_pdl(match_tc_kernel, dim3(pl.tmax[0] + (both ? pl.tmax[1] : 0), P), dim3(MT_THREADS), (size_t)MT_SMEM, s, ma));
   } else if (want_nn) {
     LTR_CUDA_TRY(cudaMemsetAsync(out.counts, 0, sizeof(int) * P, s));
+    LTR_CUDA_TRY(cudaMemsetAsync(pl.done, 0, sizeof(int), s));
   }
   if (want_nn && pl.mx[0] > 0) {
     MatchTailArgs ta{};
@@ -771,6 +775,13 @@ static int run_match_tc(const LtrMatchInput& in, const LtrMatchOutput& out, cons
     ta.thr = in.nn_thresh; ta.mutual = in.mutual;
     ta.matches0 = out.matches0; ta.scores0 = out.scores0; ta.nn1 = out.nn1; ta.counts = out.counts;
     ta.max0 = pl.mx[0];
+    ta.done = pl.done; ta.n_pairs = P; ta.world = 1;
+    if (out.gather && out.gather->world > 1) {
+      const LtrPeerGather& g = *out.gather;
+      ta.mc_base = reinterpret_cast<int*>(g.mc_base);
+      ta.peer_bases = reinterpret_cast<int* const*>(g.peer_bases);
+      ta.rank = g.rank; ta.world = g.world; ta.gslot = g.slot; ta.epoch = g.epoch;
+    }
     LaunchScope ls(KC_MATCH_TAIL, s);
     LTR_CUDA_TRY(launch_pdl(match_tail_kernel, dim3(cdiv(pl.mx[0] + (in.mutual ? pl.mx[1] : 0), 256), P), dim3(256), 0, s, ta));
   }
@@ -797,6 +808,13 @@ int ltr_match(const LtrMatchInput* in, const LtrMatchOutput* out, int32_t device
     return set_error(LTR_E_INVALID, "ltr_match: matches0 needs scores0, nn1 and counts");
   if (!want_nn && !out->dist_key) return set_error(LTR_E_INVALID, "ltr_match: nothing to compute (matches0 and dist_key are NULL)");
   if (seg && (!out->dist_sub || !out->dist_key)) return set_error(LTR_E_INVALID, "ltr_match: keyline merging needs dist_sub and dist_key");
+  if (out->gather && out->gather->world > 1) {
+    const LtrPeerGather& g = *out->gather;
+    if (seg || !tc || !want_nn) return set_error(LTR_E_UNSUPPORTED, "ltr_match: gather needs d == 256, no keyline merging, matches0");
+    if ((!g.mc_base && !g.peer_bases) || g.rank < 0 || g.rank >= g.world || g.slot < 0 || g.slot >= LTR_GATHER_SLOTS || g.epoch <= 0)
+      return set_error(LTR_E_INVALID, "ltr_match: bad LtrPeerGather");
+    if ((in->cu0 ? in->max_n0 : in->n0) <= 0) return set_error(LTR_E_UNSUPPORTED, "ltr_match: gather needs a non-empty side 0");
+  }
   if (!tc && !out->dist_key) return set_error(LTR_E_INVALID, "ltr_match: dist_key is required when d != 256");
   LTR_CUDA_TRY(cudaSetDevice(device));
   cudaStream_t s = as_stream(stream);
@@ -836,6 +854,18 @@ int ltr_match(const LtrMatchInput* in, const LtrMatchOutput* out, int32_t device
   na.n0 = in->n0; na.n1 = in->n1; na.thr = in->nn_thresh; na.mutual = in->mutual;
   na.matches0 = out->matches0; na.scores0 = out->scores0; na.nn1 = out->nn1; na.counts = out->counts;
   return run_nn(na, in->n_pairs, mk0, mk1, s);
+}
+
+int ltr_gather_wait(const void* local_base, int32_t world, int32_t n_pairs, int32_t slot, int32_t epoch, int32_t* out,
+                    int32_t device, void* stream) {
+  if (!local_base || !out || world < 1 || world > 256 || n_pairs < 1 || slot < 0 || slot >= LTR_GATHER_SLOTS)
+    return set_error(LTR_E_INVALID, "ltr_gather_wait: bad argument");
+  LTR_CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = as_stream(stream);
+  LaunchScope ls(KC_MUTUAL, s);
+  LTR_CUDA_TRY(launch_pdl(gather_wait_kernel, dim3(1), dim3(256), 0, s, reinterpret_cast<const int*>(local_base), world, n_pairs, slot,
+                          epoch, out));
+  return LTR_OK;
 }
 
 int ltr_match_distmat(const float* dist, int32_t n_pairs, int32_t n0, int32_t n1, int64_t dist_pair_stride, float nn_thresh,

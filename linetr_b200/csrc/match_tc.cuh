@@ -61,6 +61,7 @@ struct MatchTcArgs {
   float* dist;           // optional dense output of side 0 vs side 1, pair p at p * dist_stride, row-major [n0_p, n1_p]
   long long dist_stride;
   int* counts;           // zeroed here (the tail kernel accumulates into it)
+  int* done;             // tail-kernel block counter (last-block detection), zeroed here
   int n_pairs;
 };
 
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tc_kernel(MatchTcArgs p) 
   side_range(SB, pair, bb, eb);
   const int na = ea - ba, nb = eb - bb;
   if (p.counts && blockIdx.x == 0 && tid == 0) p.counts[pair] = 0;
+  if (p.done && blockIdx.x == 0 && pair == 0 && tid == 0) *p.done = 0;
   const bool active = rb * 128 < na && nb > 0;   // uniform per CTA
   const int n_ct = active ? (nb + 127) >> 7 : 0;
 
@@ -373,7 +375,21 @@ struct MatchTailArgs {
   float thr; int mutual;
   int* matches0; float* scores0; int* nn1; int* counts;
   int max0;                        // max lines of side 0 per pair (row part of the grid)
+  // multi-GPU publication of `counts` (LtrPeerGather): symmetric buffer = counts[SLOTS][world][n_pairs] | flags[SLOTS][world]
+  int* done;                       // block counter for last-block detection
+  int* mc_base; int* const* peer_bases;
+  int rank, world, gslot, epoch, n_pairs;
 };
+
+constexpr int GATHER_SLOTS = 4;
+__device__ __forceinline__ void multimem_st_u32(int* mc_addr, int v) {
+  asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // Exact fp32 distances of line `r` of side `sa` to every line of the other side (ascending-k fmaf chain,
 // the arithmetic of the round-1 FFMA matcher), first-minimum argmin over them; whole warp.
@@ -517,6 +533,49 @@ __global__ void __launch_bounds__(256) match_tail_kernel(MatchTailArgs p) {
   }
   __syncthreads();
   if (tid == 0 && n_keep) atomicAdd(&p.counts[pair], n_keep);
+  if (p.world > 1) {
+    // ---- fused collective: the LAST block of the grid publishes this rank's counts to every rank over NVLink ----
+    __shared__ int is_last;
+    if (tid == 0) {
+      __threadfence();
+      is_last = atomicAdd(p.done, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const long long cnt_off = ((long long)p.gslot * p.world + p.rank) * p.n_pairs;
+      const long long flag_off = (long long)GATHER_SLOTS * p.world * p.n_pairs + (long long)p.gslot * p.world + p.rank;
+      for (int i = tid; i < p.n_pairs; i += 256) {
+        const int v = __ldcg(p.counts + i);
+        if (p.mc_base) multimem_st_u32(p.mc_base + cnt_off + i, v);
+        else
+          for (int r = 0; r < p.world; ++r) p.peer_bases[r][cnt_off + i] = v;
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        if (p.mc_base) multimem_st_u32(p.mc_base + flag_off, p.epoch);
+        else
+          for (int r = 0; r < p.world; ++r) *reinterpret_cast<volatile int*>(p.peer_bases[r] + flag_off) = p.epoch;
+        __threadfence_system();
+      }
+    }
+  }
+}
+
+// one block: wait until every rank's flag of the slot reached `epoch`, then copy the gathered counts out
+__global__ void __launch_bounds__(256) gather_wait_kernel(const int* base, int world, int n_pairs, int slot, int epoch, int* out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int* flags = base + (long long)GATHER_SLOTS * world * n_pairs + (long long)slot * world;
+  if ((int)threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + threadIdx.x) < epoch)
+      if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s: a rank died - fail loudly instead of hanging
+  }
+  __syncthreads();
+  const int* src = base + (long long)slot * world * n_pairs;
+  for (int i = threadIdx.x; i < world * n_pairs; i += 256) out[i] = __ldcv(src + i);
 }
 
 }  // namespace ltr

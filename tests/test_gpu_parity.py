@@ -694,3 +694,18 @@ def test_host_pipelined_entry_with_keyline_merging():
     for p, (a, b) in enumerate(pairs):
         mat, _, _, _ = orc.match_pair(sd, a, b, 0.8)
         assert np.array_equal(want.pair(p).cpu().numpy(), orc.match_indices(mat))
+
+
+def test_peer_counts_fused_gather_world2():
+    """Multi-GPU (needs >= 2 GPUs on the box): the match counts published to every rank by the matcher's tail
+    kernel (multimem.st / peer stores over NVLink, no collective kernel) equal an ncclAllGather of them."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29577", os.path.join(root, "tools", "peer_counts_check.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, (out.stdout[-3000:], out.stderr[-3000:])

@@ -1,0 +1,39 @@
+"""clock64 timeline of CTA 0 of the LAST chained GEMM launch of an encode (mlp1 -> mlp2 -> final_proj of
+signature layer 6; 2 + 1 + 1 tiles) - MMA issue, accumulator ready, epilogue done, op-boundary waits.
+LTR_GEMM_PAIR=0/1 selects the engine."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from linetr_b200 import LineBatch, LineTransformer, PairEngine, _native as N, synthetic as syn
+
+lib = N.load()
+dev = torch.device("cuda", 0)
+sd = syn.make_state_dict(0, 1)
+m = LineTransformer({"mode": "train"})
+m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+m = m.eval().to(dev)
+eng = PairEngine(m, dev)
+b = LineBatch.from_images([syn.make_image_inputs(i, 128, 21) for i in range(128)]).to(dev)
+for _ in range(3):
+    eng.encode(b)
+torch.cuda.synchronize()
+lib.ltr_debug_trace_arm(1)
+eng.encode(b)
+torch.cuda.synchronize()
+buf = (C.c_uint64 * 128)()
+lib.ltr_debug_trace_read(buf)
+lib.ltr_debug_trace_arm(0)
+t0 = buf[110]
+print("engine:", "pair" if os.environ.get("LTR_GEMM_PAIR", "1") != "0" else "single", " t0 = after pdl_wait")
+names = ["mlp1 nb0 (K512)", "mlp1 nb1 (K512)", "mlp2 (K512)", "final (K256, norm)"]
+for tl, nm in enumerate(names):
+    a = [buf[40 + tl * 4 + i] for i in range(4)]
+    af = buf[80 + tl]
+    print(f"{nm:20s} acc_empty ok +{a[0]-t0:7d} | first operands +{a[1]-t0:7d} | MMAs committed +{a[2]-t0:7d} | "
+          f"epilogue sees acc +{af-t0:7d} | epilogue done +{a[3]-t0:7d}   (mma loop {a[2]-a[1]}, epilogue {a[3]-af})")
+for d in (1, 2):
+    print(f"producer: op boundary {d} passed at +{buf[100 + d] - t0}")
