@@ -645,7 +645,17 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
 // M = 256 (128 rows per CTA) x N = 256: 64 KB per SM per k-block = 41.7 B/cycle/SM.
 //   barriers: full (local TMA) + peer_full (peer's stage landed, relayed by the peer's otherwise idle MMA warp
 //   with a remote arrive), empty / acc_full (tcgen05.commit multicast to both CTAs), acc_empty (leader, 16
-//   arrivals: the 8 epilogue warps of each CTA), op_done (local, as in gemm_chain_kernel).
+//   arrivals: the 8 epilogue warps of each CTA).
+// Epilogue and op-to-op dependencies.  The trace of the first version (profiles/r2_chain_trace.md) showed the
+// MMA loop at the tensor peak but only 45 % of the launch inside it: at every op boundary the next op waited
+// for the WHOLE epilogue of the previous op's last tile (8-12 k cycles through per-warp staging + LDS + STG)
+// plus a fence and a TMA round trip.  Now image-only tiles are drained in k-block order: all 8 epilogue warps
+// work on the same 64-column k-block, write its hi / lo planes into one 32 KB staging tile in the image's own
+// swizzled layout and ONE thread stores them with two 16 KB bulk copies (TMA store); a shared sequence counter
+// `seq_done` publishes every finished output k-block, and the producer of the NEXT op loads A k-block j as
+// soon as output k-block j of the previous op is in memory - the next op's MMAs start while the previous
+// tile is still being drained.  Tiles with fp32 row outputs / residuals or the row-norm epilogue keep the
+// per-warp staging path and publish their four k-blocks at the end.
 struct GemmPairCfg {
   static constexpr int BN = 256;
   static constexpr int A_TILE = 16384;
@@ -691,8 +701,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
   uint64_t* empty = peer_full + Cfg::STAGES;      // [3] local, multicast commit
   uint64_t* acc_full = empty + Cfg::STAGES;       // [2] local, multicast commit
   uint64_t* acc_empty = acc_full + 2;             // [2] used in the leader, 16 arrivals
-  uint64_t* op_done = acc_empty + 2;              // [1] local
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_done + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile uint32_t* seq_done = tmem_slot + 1;    // output k-blocks (64 columns of one m-tile) completed by this CTA's epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -710,7 +720,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
       ptx::mbar_init(&acc_full[b], 1);
       ptx::mbar_init(&acc_empty[b], 16);
     }
-    ptx::mbar_init(op_done, 8);
+    *seq_done = 0;
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -728,21 +738,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs: own A tile, own half of W)
     if (lane == 0) {
-      uint32_t it = 0, dep = 0;
+      uint32_t it = 0, seq_prev = 0, seq_base = 0;   // seq_prev: sequence number of the previous op's first output k-block
       for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
         const int mt = 2 * ct + (int)rank;
         for (int o = 0; o < c.n_ops; ++o) {
           const GemmImgArgs& p = c.op[o];
-          if (o > 0) {
-            mbar_wait_dl(op_done, dep & 1, false);
-            ++dep;
-            if (dep < 8) LTR_DBG_STAMP(100 + dep);
-          }
           const int nk = p.W.K / 64;
           const uint8_t* whi = reinterpret_cast<const uint8_t*>(p.W.hi);
           const uint8_t* wlo = reinterpret_cast<const uint8_t*>(p.W.lo);
           for (int nb = 0; nb < p.n_blks; ++nb)
             for (int kb = 0; kb < nk; ++kb, ++it) {
+              if (o > 0 && nb == 0) {
+                // A k-block kb of this op = output k-block kb of the previous op (same m-tile, same CTA): wait until
+                // the epilogue has published it (bulk store completed / generic stores fenced)
+                const uint32_t need = seq_prev + (uint32_t)kb + 1;
+                if (*seq_done < need) {
+                  const long long t0 = clock64();
+                  while (*seq_done < need)
+                    if (clock64() - t0 > 4000000000LL) __trap();
+                }
+                __threadfence_block();
+                ptx::fence_proxy_async_all();
+                if (kb == 0 && o < 8) LTR_DBG_STAMP(100 + o);
+              }
               const int s = it % Cfg::STAGES;
               const uint32_t ph = (it / Cfg::STAGES) & 1;
               mbar_wait_dl(&empty[s], ph ^ 1, true);
@@ -755,6 +773,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
               ptx::bulk_g2s(st + 2 * Cfg::A_TILE, whi + woff, Cfg::W_HALF, &full[s]);
               ptx::bulk_g2s(st + 2 * Cfg::A_TILE + Cfg::W_HALF, wlo + woff, Cfg::W_HALF, &full[s]);
             }
+          seq_prev = seq_base;
+          seq_base += 4u * (uint32_t)p.n_blks;
         }
       }
     }
@@ -817,39 +837,121 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
     // ---------------------------------------------------------------- epilogue (8 warps per CTA, own 128 rows)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (warp - 2) * Cfg::STG_WARP);
+    const bool elected = warp == 2 && lane == 0;   // issues the bulk stores and publishes seq_done
+    uint8_t* tile = smem + Cfg::OFF_STG;            // streamed path: [hi 16 KB | lo 16 KB] of one output k-block
+    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (warp - 2) * Cfg::STG_WARP);   // staged path: per-warp 4 KB
     uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
-    uint32_t tl = 0;
+    const int r_in = q * 32 + lane;
+    uint32_t tl = 0, pending = 0;                   // pending: k-blocks whose bulk stores the elected thread has in flight
+    auto publish_pending = [&]() {                  // elected thread only
+      if (pending) {
+        ptx::bulk_wait_all();
+        __threadfence_block();
+        *seq_done = *seq_done + pending;
+        pending = 0;
+      }
+    };
     for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
       const int mt = 2 * ct + (int)rank;
       for (int o = 0; o < c.n_ops; ++o) {
         const GemmImgArgs& p = c.op[o];
+        const bool streamed = p.norm == NORM_NONE && p.O.hi && !p.C && !p.R;
         for (int nb = 0; nb < p.n_blks; ++nb, ++tl) {
           const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
           mbar_wait_dl(&acc_full[buf], aph, true);
           ptx::tc_fence_after();
           const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
           if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(80 + tl);
-          if (p.norm != NORM_NONE)
-            epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
-          else
-            epi_plain_tile<BN>(p, tacc, mt, nb, q, half, lane, stg, stgb);
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(43 + tl * 4);
-          if (lane == 0) {
-            if (leader) ptx::mbar_arrive(&acc_empty[buf]);
-            else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
+          if (streamed) {
+#pragma unroll 1
+            for (int kbl = 0; kbl < 4; ++kbl) {
+              const int c0 = kbl * 64 + half * 32, nbase = nb * BN + c0;
+              float acc[32];
+              ptx::tmem_ld32(tacc + (uint32_t)c0, acc);
+              if (kbl == 3) {   // this warp has read everything it needs from the accumulator
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (leader) ptx::mbar_arrive(&acc_empty[buf]);
+                  else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
+                }
+              }
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b = *reinterpret_cast<const float4*>(p.bias + nbase + j);
+                  acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
+                }
+              }
+              if (p.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+              } else if (p.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+              }
+              if (p.Rimg.hi) {   // residual straight from the split-bf16 image (own row, 4 x 16 B per plane)
+                const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
+                const uint8_t* rhi = reinterpret_cast<const uint8_t*>(p.Rimg.hi + rtoff);
+                const uint8_t* rlo = reinterpret_cast<const uint8_t*>(p.Rimg.lo + rtoff);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                  const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);
+                  const uint4 vh = *reinterpret_cast<const uint4*>(rhi + off);
+                  const uint4 vl = *reinterpret_cast<const uint4*>(rlo + off);
+                  const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
+                    acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
+                  }
+                }
+              }
+              uint4 h[4], l[4];
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) ptx::split8_bf16(&acc[cc * 8], h[cc], l[cc]);
+              if (elected) publish_pending();       // the staging tile's previous bulk stores are complete
+              epi_bar();                            // ... and everybody knows it
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);
+                *reinterpret_cast<uint4*>(tile + off) = h[cc];
+                *reinterpret_cast<uint4*>(tile + 16384 + off) = l[cc];
+              }
+              ptx::fence_proxy_async_smem();
+              epi_bar();
+              if (elected) {
+                const size_t toff = ((size_t)mt * p.O.kblocks + p.o_kb0 + nb * 4 + kbl) * IMG_TILE_ELEMS;
+                ptx::bulk_s2g(p.O.hi + toff, tile, 16384);
+                ptx::bulk_s2g(p.O.lo + toff, tile + 16384, 16384);
+                ptx::bulk_commit();
+                pending = 1;
+              }
+            }
+          } else {
+            if (elected) publish_pending();         // the per-warp staging areas alias the streamed tile
+            epi_bar();
+            if (p.norm != NORM_NONE)
+              epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
+            else
+              epi_plain_tile<BN>(p, tacc, mt, nb, q, half, lane, stg, stgb);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) ptx::mbar_arrive(&acc_empty[buf]);
+              else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
+            }
+            // generic-proxy global stores of this tile -> visible to the bulk copies of the next op's producer
+            __threadfence();
+            ptx::fence_proxy_async_all();
+            epi_bar();
+            if (elected) *seq_done = *seq_done + 4;
           }
-        }
-        if (o + 1 < c.n_ops) {
-          __threadfence();
-          ptx::fence_proxy_async_all();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(op_done);
+          if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(43 + tl * 4);
         }
       }
     }
+    if (elected) publish_pending();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -931,6 +1033,9 @@ inline int launch_gemm_chain(const GemmImgArgs* ops, int n_ops, cudaStream_t s, 
       return set_error(-1, "gemm_chain: k-block range exceeds an image");
     if (a.norm != NORM_NONE && (a.W.N != 256 || a.Rimg.hi || a.act != ACT_NONE))
       return set_error(-1, "gemm_chain: the row-norm epilogue needs N == 256, no activation, fp32 residual");
+    // op i > 0 reads, k-block for k-block, what op i-1 wrote for the same rows (the kernels' dependency rule)
+    if (i > 0 && (a.A.hi != ops[i - 1].O.hi || a.a_kb0 != ops[i - 1].o_kb0 || a.W.K > ops[i - 1].W.N))
+      return set_error(-1, "gemm_chain: op i must consume the image op i-1 writes (same k-blocks)");
     a.m_tiles = c.m_tiles;
     a.n_blks = a.W.N / 256;
     c.op[i] = a;

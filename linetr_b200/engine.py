@@ -177,7 +177,7 @@ class PairEngine:
         return (res[1], res[0]) if want_cf else res[1]
 
     def match_pairs(self, side0: LineBatch, side1: LineBatch, nn_thresh: Optional[float] = None, mutual=True,
-                    keep_desc=False, want_dist=False) -> PairMatches:
+                    keep_desc=False, want_dist=False, gather=None) -> PairMatches:
         """want_dist=True also returns the key-line distance matrices (`Matching`'s
         'matching_scores_l'); by default they are never materialised (the row argmin lives in the
         epilogue of the tensor-core contraction) unless key-line merging needs them."""
@@ -220,13 +220,14 @@ class PairEngine:
                       max_n0=int(np.diff(side0.cu_lines).max(initial=0)), max_n1=int(np.diff(side1.cu_lines).max(initial=0)),
                       total_k0=side0.n_lines, total_k1=side1.n_lines)
             off0 = side0.cu_lines
-        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, want_dist=want_dist, **kw)
+        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, want_dist=want_dist,
+                                     gather=gather, **kw)
         return PairMatches(out["matches0"], out["scores0"], out["counts"], np.asarray(off0, dtype=np.int32),
                            out["dist_key"], out["stride"], d0 if keep_desc else None, d1 if keep_desc else None)
 
 
     def match_packed(self, batch: LineBatch, n_pairs: int, nn_thresh: Optional[float] = None, mutual=True,
-                     keep_desc=False, want_dist=False) -> PairMatches:
+                     keep_desc=False, want_dist=False, gather=None) -> PairMatches:
         """Same as match_pairs for a batch that holds BOTH sides: images [0, P) are the side-0
         images of the P pairs, images [P, 2P) their side-1 partners.  One `ltr_encode` over all
         2P images (twice the rows per GEMM launch) and one `ltr_match`."""
@@ -273,7 +274,8 @@ class PairEngine:
                                              total_k0=R0, total_k1=int(cu[-1]) - R0)
             kw = batch._dev_cache[key]
             off0 = cu[:P + 1]
-        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, want_dist=want_dist, **kw)
+        out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, float(nn_thresh), mutual, want_dist=want_dist,
+                                     gather=gather, **kw)
         return PairMatches(out["matches0"], out["scores0"], out["counts"], np.asarray(off0, dtype=np.int32),
                            out["dist_key"], out["stride"], d0 if keep_desc else None, d1 if keep_desc else None)
 
@@ -360,3 +362,65 @@ def gather_counts(local_counts: torch.Tensor, n_total: int, group=None, async_op
     gathered = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(gathered, buf, group=group)
     return torch.cat([g[:e - s] for g, (s, e) in zip(gathered, sizes)])
+
+
+class PeerCounts:
+    """The path's one collective without a collective kernel: a symmetric int32 buffer (peer-mapped over
+    NVLink with torch.distributed._symmetric_memory) into which the matcher's tail kernel of every rank
+    stores its per-pair match counts for ALL ranks - `multimem.st` through the NVSwitch multicast address
+    when the allocation supports it, plain peer stores otherwise (include/linetr_b200.h: LtrPeerGather).
+
+        pc = PeerCounts(n_pairs_per_rank)                            # collective: allocation + rendezvous
+        res = eng.match_packed(batch, P, 0.8, gather=pc.publish())   # counts published by the tail kernel
+        ...                                                          # (at most GATHER_SLOTS - 2 publishes in flight)
+        all_counts = pc.collect()                                    # [world * n_pairs] of the OLDEST uncollected publish
+    """
+
+    def __init__(self, n_pairs: int, group=None, device=None, multicast=True):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if not (dist.is_available() and dist.is_initialized()):
+            raise N.LtrError("PeerCounts needs an initialised torch.distributed process group (NCCL)")
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.n_pairs = dist.get_world_size(group), dist.get_rank(group), int(n_pairs)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        n = N.GATHER_SLOTS * self.world * (self.n_pairs + 1)
+        self.buf = symm_mem.empty(n, dtype=torch.int32, device=self.device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)                      # every rank's flags are zero before anybody publishes
+        mc = 0
+        try:
+            if multicast and self.hdl.has_multicast_support:
+                mc = int(self.hdl.multicast_ptr)
+        except Exception:
+            mc = 0
+        self.multicast = mc != 0
+        self._mc = mc
+        self._peers = int(self.hdl.buffer_ptrs_dev)
+        self._published = 0
+        self._collected = 0
+
+    def publish(self) -> "N.LtrPeerGather":
+        """Descriptor for the next ltr_match call (pass as `gather=`)."""
+        if self._published - self._collected >= N.GATHER_SLOTS - 2:
+            raise N.LtrError("PeerCounts: collect() earlier publishes first (at most GATHER_SLOTS - 2 in flight)")
+        e = self._published
+        self._published += 1
+        return N.LtrPeerGather(self._mc or None, self._peers, self.rank, self.world, e % N.GATHER_SLOTS, e // N.GATHER_SLOTS + 1)
+
+    def collect(self) -> torch.Tensor:
+        """Counts of all ranks for the oldest publish not collected yet, int32 [world * n_pairs]; enqueues one
+        tiny kernel on the current stream that waits for the world's flags (no host synchronisation)."""
+        if self._collected >= self._published:
+            raise N.LtrError("PeerCounts.collect(): nothing published")
+        e = self._collected
+        self._collected += 1
+        out = torch.empty(self.world * self.n_pairs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = N.load().ltr_gather_wait(C.c_void_p(self.buf.data_ptr()), self.world, self.n_pairs, e % N.GATHER_SLOTS,
+                                          e // N.GATHER_SLOTS + 1, C.c_void_p(out.data_ptr()), self.device.index,
+                                          C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        N.check(rc, "ltr_gather_wait")
+        return out
