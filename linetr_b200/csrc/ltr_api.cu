@@ -15,6 +15,7 @@
 #include "gemm_img.cuh"
 #include "token_fused.cuh"
 #include "sig_attention_tc.cuh"
+#include "sig_attention_img.cuh"
 #include "tokenizer_kernels.cuh"
 #include "match_kernels.cuh"
 #include "match_tc.cuh"
@@ -276,6 +277,14 @@ static int chain_min_tiles() {
   }();
   return v;
 }
+// LTR_ATTN_IMG=0 keeps uniform 128-line batches on the general attention kernel (one CTA per image and head).
+static bool attn_img() {
+  static const bool v = [] {
+    const char* e = std::getenv("LTR_ATTN_IMG");
+    return e ? std::atoi(e) != 0 : true;
+  }();
+  return v;
+}
 // LTR_GEMM_PAIR=0 runs the chains on the single-CTA engine instead of the CTA-pair (cta_group::2) one.
 static bool gemm_pair() {
   static const bool v = [] {
@@ -373,7 +382,9 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   for (size_t li = 0; li < m->sig.size(); ++li) {
     const SigLayer& L = m->sig[li];
     if (!chain || (li == 0 && !chain_line)) LTR_TRY(gemm(L.qkv, w.xm, 0, R, ACT_NONE, s, nullptr, 0, &w.qkv, 0));
-    LTR_TRY(launch_sig_attention_tc(w.qkv, w.xm, 256, cu, in.lines_per_image, max_l, in.n_images, s));  // o -> xm[:, 256:]
+    // o -> xm[:, 256:]; images of exactly 128 lines are the 128-row tiles of the qkv image: per-image pipelined kernel
+    if (!cu && in.lines_per_image == 128 && attn_img()) LTR_TRY(launch_sig_attention_img(w.qkv, w.xm, 256, in.n_images, s));
+    else LTR_TRY(launch_sig_attention_tc(w.qkv, w.xm, 256, cu, in.lines_per_image, max_l, in.n_images, s));
     // x += delta: the running descriptor lives ONLY as the split-bf16 image xm[:, :256] (hi + lo carries
     // ~2^-17 relative precision; an fp32 copy would double the store traffic of this epilogue)
     if (chain) {
