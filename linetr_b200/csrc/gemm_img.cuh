@@ -928,6 +928,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
                 pending = 1;
               }
             }
+            // the tile's last k-block must be published NOW: the next op's MMAs (whose accumulator the epilogue
+            // waits for next) need it as an operand
+            if (elected) publish_pending();
           } else {
             if (elected) publish_pending();         // the per-warp staging areas alias the streamed tile
             epi_bar();

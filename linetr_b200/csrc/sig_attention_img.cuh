@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(SigImgCfg::THREADS, 1) sig_attention_img_kerne
   auto t_s = [&](int s) { return tmem_base + (uint32_t)s * 128; };          // S[s]: 128 columns
   auto t_o = [&](int s) { return tmem_base + 256 + (uint32_t)s * 64; };     // O[s]: 64 columns
   pdl_wait();   // the qkv image of this layer is complete; the previous reader of `out` is done
+  if (tid == 0) LTR_DBG_STAMP(112);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer: q, k, v tiles of head h
@@ -133,7 +134,14 @@ __global__ void __launch_bounds__(SigImgCfg::THREADS, 1) sig_attention_img_kerne
         }
         ptx::umma_commit(&o_done[s]);
       };
-      issue_s(0); issue_s(1); issue_pv(0); issue_s(2); issue_pv(1); issue_s(3); issue_pv(2); issue_pv(3);
+      issue_s(0); LTR_DBG_STAMP(113);
+      issue_s(1); LTR_DBG_STAMP(114);
+      issue_pv(0); LTR_DBG_STAMP(115);
+      issue_s(2); LTR_DBG_STAMP(116);
+      issue_pv(1); LTR_DBG_STAMP(117);
+      issue_s(3); LTR_DBG_STAMP(118);
+      issue_pv(2); LTR_DBG_STAMP(119);
+      issue_pv(3); LTR_DBG_STAMP(120);
     }
   } else {
     // ---------------------------------------------------------------- softmax + epilogue (16 warps)
@@ -197,7 +205,15 @@ __global__ void __launch_bounds__(SigImgCfg::THREADS, 1) sig_attention_img_kerne
         img_store8(out, img * 128 + row, (out_kb0 + h) * 64 + part * 16 + j, w);
       }
     };
-    softmax(0); softmax(1); epilogue(0); softmax(2); epilogue(1); softmax(3); epilogue(2); epilogue(3);
+    const bool st = warp == 2 && lane == 0;
+    softmax(0); if (st) LTR_DBG_STAMP(121);
+    softmax(1); if (st) LTR_DBG_STAMP(122);
+    epilogue(0); if (st) LTR_DBG_STAMP(123);
+    softmax(2); if (st) LTR_DBG_STAMP(124);
+    epilogue(1);
+    softmax(3); if (st) LTR_DBG_STAMP(125);
+    epilogue(2);
+    epilogue(3); if (st) LTR_DBG_STAMP(126);
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
   uint64_t* acc_ready = bars + 5;   // MMA -> workers: accumulator complete (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   uint64_t* dbar = bars + 8;        // [4] descriptor columns {32 s .. 32 s + 32} u {128 + 32 s ..} of the tile have landed
+  uint64_t* l5_done = bars + 12;    // MMA -> MMA thread: all L5 MMAs complete (last descriptor group may be fetched)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
     ptx::mbar_init(a_ready, 256);
     ptx::mbar_init(acc_ready, 1);
     for (int i = 0; i < 4; ++i) ptx::mbar_init(&dbar[i], 1);
+    ptx::mbar_init(l5_done, 1);
     ptx::prefetch_tensormap(&desc_map);
     ptx::fence_mbar_init();
   }
@@ -143,8 +145,8 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
         push(p.W3, 0, 0);
         for (int nb = 0; nb < 2; ++nb)
           for (int kb = 0; kb < 2; ++kb) push(p.W4, nb, kb);
-        for (int nb = 0; nb < 2; ++nb)
-          for (int kb = 0; kb < 4; ++kb) push(p.W5, nb, kb);
+        for (int kb = 0; kb < 4; ++kb)       // L5: k-block outer (see the MMA issuer: frees the A tiles early)
+          for (int nb = 0; nb < 2; ++nb) push(p.W5, nb, kb);
       }
     }
   } else if (warp == 1) {
@@ -176,7 +178,21 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
         ptx::umma_commit(&empty[s]);
         ++it;
       };
+      // The tile's sampled descriptors ([128 token rows x 256] fp32 - the one mandatory HBM stream of this stage) land
+      // in the activation region, which holds the L5 A operand (h256) until L5's MMAs have read it.  Column group
+      // s (blocks s and 4 + s of 32 columns) occupies exactly the memory of h256's k-block s (hi and lo tile), so L5
+      // runs k-block outer / n-block inner and group s is fetched as soon as both MMA blocks of k-block s are
+      // complete - which this thread knows without extra barriers: the 2-slot W ring made it wait for them before it
+      // could issue the blocks of k-block s + 1.  Three of the four groups (96 KB) stream in under L5's own MMAs.
+      float* xs_t = reinterpret_cast<float*>(act);
+      uint32_t nl5 = 0;
+      auto issue_desc = [&](int sgrp, int tok0) {
+        ptx::mbar_arrive_expect_tx(&dbar[sgrp], 2 * 16384);
+        ptx::tma_load_2d(xs_t + sgrp * 4096, &desc_map, sgrp * 32, tok0, &dbar[sgrp]);
+        ptx::tma_load_2d(xs_t + (4 + sgrp) * 4096, &desc_map, (4 + sgrp) * 32, tok0, &dbar[sgrp]);
+      };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int tok0 = (int)((long long)tile * p.lpt * p.T);
         ptx::mbar_wait(a_ready, na++ & 1);   // h64
         ptx::tc_fence_after();
         block(1, 0, 0, true);
@@ -188,9 +204,14 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
         ptx::umma_commit(acc_ready);
         ptx::mbar_wait(a_ready, na++ & 1);   // h256
         ptx::tc_fence_after();
-        for (int nb = 0; nb < 2; ++nb)
-          for (int kb = 0; kb < 4; ++kb) block(4, kb, nb, kb == 0);
+        for (int kb = 0; kb < 4; ++kb) {
+          for (int nb = 0; nb < 2; ++nb) block(4, kb, nb, kb == 0);
+          if (kb >= 1) issue_desc(kb - 1, tok0);   // both blocks of k-block kb-1 are complete: their A tiles are dead
+        }
         ptx::umma_commit(acc_ready);
+        ptx::umma_commit(l5_done);
+        ptx::mbar_wait(l5_done, nl5++ & 1);
+        issue_desc(3, tok0);
       }
     }
   } else {
@@ -254,7 +275,6 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
     };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int line0 = tile * p.lpt;
-      const long long tok0 = (long long)line0 * p.T;
       const bool tr = (tile == blockIdx.x + gridDim.x) && warp == 2 && lane == 0;   // trace the CTA's 2nd tile
       if (tr) LTR_DBG_STAMP(0);
       // ---- P0 result of THIS tile (computed during the previous tile's L5 MMAs) -> h64 operand tile
@@ -310,19 +330,10 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       ptx::tc_fence_after();
       if (tr) LTR_DBG_STAMP(6);
       float* xs = reinterpret_cast<float*>(act);
-      // phase A: the tile's descriptors ([128 token rows x 256] fp32, the one mandatory HBM stream of this
-      // stage) -> the (now dead) activation region by TMA: eight
-      // SWIZZLE_128B boxes of 32 columns, issued as four groups in the order the epilogue consumes
-      // them (group s = column blocks s and 4 + s), one mbarrier per group.  Rows past the end of the
-      // batch are zero-filled by the TMA unit; rows of the next tile that ride along are never used.
-      if (wt == 0) {
-#pragma unroll
-        for (int sgrp = 0; sgrp < 4; ++sgrp) {
-          ptx::mbar_arrive_expect_tx(&dbar[sgrp], 2 * 16384);
-          ptx::tma_load_2d(xs + sgrp * 4096, &desc_map, sgrp * 32, (int)tok0, &dbar[sgrp]);
-          ptx::tma_load_2d(xs + (4 + sgrp) * 4096, &desc_map, (4 + sgrp) * 32, (int)tok0, &dbar[sgrp]);
-        }
-      }
+      // phase A: the tile's descriptors arrive in the (dead) activation region by TMA - eight SWIZZLE_128B
+      // boxes of 32 columns in four groups (group s = column blocks s and 4 + s, one mbarrier per group),
+      // issued by the MMA thread while L5 still runs (see there).  Rows past the end of the batch are
+      // zero-filled by the TMA unit; rows of the next tile that ride along are never used.
       if (tr) LTR_DBG_STAMP(12);
       float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
 #pragma unroll 1

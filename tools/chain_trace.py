@@ -37,3 +37,10 @@ for tl, nm in enumerate(names):
           f"epilogue sees acc +{af-t0:7d} | epilogue done +{a[3]-t0:7d}   (mma loop {a[2]-a[1]}, epilogue {a[3]-af})")
 for d in (1, 2):
     print(f"producer: op boundary {d} passed at +{buf[100 + d] - t0}")
+
+# per-image attention kernel (last layer): MMA thread issue times and the softmax warps' progress
+a0 = buf[112]
+if a0:
+    nm = ["S0 issued", "S1 issued", "PV0 issued", "S2 issued", "PV1 issued", "S3 issued", "PV2 issued", "PV3 issued",
+          "softmax0 done", "softmax1 done", "epilogue0 done", "softmax2 done", "softmax3 done", "epilogue3 done"]
+    print("sig_attention_img CTA 0 (cycles after pdl_wait):", ", ".join(f"{n} +{buf[113 + i] - a0}" for i, n in enumerate(nm)))
