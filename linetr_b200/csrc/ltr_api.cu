@@ -277,11 +277,12 @@ static int chain_min_tiles() {
   }();
   return v;
 }
-// LTR_ATTN_IMG=0 keeps uniform 128-line batches on the general attention kernel (one CTA per image and head).
+// LTR_ATTN_IMG=1 runs uniform 128-line batches on the per-image pipelined attention kernel (sig_attention_img.cuh).
+// Off by default: measured 33.4 us per launch against 25.4 us for the general kernel (profiles/r2_attention_img.md).
 static bool attn_img() {
   static const bool v = [] {
     const char* e = std::getenv("LTR_ATTN_IMG");
-    return e ? std::atoi(e) != 0 : true;
+    return e ? std::atoi(e) != 0 : false;
   }();
   return v;
 }
