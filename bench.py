@@ -379,9 +379,8 @@ def main():
 
     def drain():
         while pending:
-            pending.pop(0)[1].wait()
-        while peer is not None and peer._collected < peer._published:
-            gathered["last"] = peer.collect()
+            h = pending.pop(0)[1]
+            gathered["last"] = h.result() if peer is not None else h.wait()
 
     def run_resident(gather=None):
         if wl == "cfg4":
@@ -394,8 +393,8 @@ def main():
     def step_resident():
         if peer is not None:
             m0, cnt = run_resident(peer.publish())
-            if peer._published - peer._collected >= 2:    # collect step i-1 behind step i: never waits in practice
-                gathered["last"] = peer.collect()
+            drain()                                      # counts of step i-1 (its D2H copy ran under step i's kernels)
+            pending.append((None, peer.collect_async())) # copy-engine D2H of this step's slot behind this step's kernels
             return m0, cnt
         m0, cnt = run_resident()
         if world > 1:

@@ -651,11 +651,14 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
 // for the WHOLE epilogue of the previous op's last tile (8-12 k cycles through per-warp staging + LDS + STG)
 // plus a fence and a TMA round trip.  Now image-only tiles are drained in k-block order: all 8 epilogue warps
 // work on the same 64-column k-block, write its hi / lo planes into one 32 KB staging tile in the image's own
-// swizzled layout and ONE thread stores them with two 16 KB bulk copies (TMA store); a shared sequence counter
-// `seq_done` publishes every finished output k-block, and the producer of the NEXT op loads A k-block j as
-// soon as output k-block j of the previous op is in memory - the next op's MMAs start while the previous
-// tile is still being drained.  Tiles with fp32 row outputs / residuals or the row-norm epilogue keep the
-// per-warp staging path and publish their four k-blocks at the end.
+// swizzled layout and a dedicated STORE WARP (warp 10) stores them with two 16 KB bulk copies (TMA store);
+// epilogue and store warp hand the staging tile back and forth through two mbarriers (tile_ready: 8 warp
+// arrivals, tile_free: the bulk copies have read the tile), so no epilogue warp ever waits for a global
+// store to complete.  The store warp also publishes every finished output k-block in the shared sequence
+// counter `seq_done`; the producer of the NEXT op loads A k-block j as soon as output k-block j of the previous
+// op is in memory - the next op's MMAs start while the previous tile is still being drained.  Tiles with fp32
+// row outputs / residuals or the row-norm epilogue keep the per-warp staging path (one hand-over per tile, four
+// k-blocks published at once).
 struct GemmPairCfg {
   static constexpr int BN = 256;
   static constexpr int A_TILE = 16384;
@@ -668,7 +671,7 @@ struct GemmPairCfg {
   static constexpr int OFF_XCH = OFF_BAR + 256;
   static constexpr int SMEM = OFF_XCH + 2048 + 768;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int THREADS = 320;
+  static constexpr int THREADS = 352;             // TMA warp, MMA / relay warp, 8 epilogue warps, store warp
 };
 static_assert(GemmPairCfg::SMEM <= 232448, "gemm pair: shared memory budget");
 
@@ -689,7 +692,7 @@ __device__ __forceinline__ void mbar_wait_dl(uint64_t* bar, uint32_t parity, boo
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {
   using Cfg = GemmPairCfg;
   constexpr int BN = Cfg::BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -701,7 +704,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
   uint64_t* empty = peer_full + Cfg::STAGES;      // [3] local, multicast commit
   uint64_t* acc_full = empty + Cfg::STAGES;       // [2] local, multicast commit
   uint64_t* acc_empty = acc_full + 2;             // [2] used in the leader, 16 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* tile_ready = acc_empty + 2;           // [1] local: the 8 epilogue warps filled the staging tile / finished a staged tile
+  uint64_t* tile_free = tile_ready + 1;           // [1] local: the store warp's bulk copies have read the staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_free + 1);
   volatile uint32_t* seq_done = tmem_slot + 1;    // output k-blocks (64 columns of one m-tile) completed by this CTA's epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -720,6 +725,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
       ptx::mbar_init(&acc_full[b], 1);
       ptx::mbar_init(&acc_empty[b], 16);
     }
+    ptx::mbar_init(tile_ready, 8);
+    ptx::mbar_init(tile_free, 1);
     *seq_done = 0;
     ptx::fence_mbar_init();
   }
@@ -833,24 +840,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
           }
         }
     }
+  } else if (warp == 10) {
+    // ---------------------------------------------------------------- store warp: staging tile -> global (TMA store), publish
+    if (lane == 0) {
+      uint8_t* tile = smem + Cfg::OFF_STG;
+      uint32_t hs = 0;
+      for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
+        const int mt = 2 * ct + (int)rank;
+        for (int o = 0; o < c.n_ops; ++o) {
+          const GemmImgArgs& p = c.op[o];
+          const bool streamed = p.norm == NORM_NONE && p.O.hi && !p.C && !p.R;
+          for (int nb = 0; nb < p.n_blks; ++nb) {
+            if (streamed) {
+              for (int kbl = 0; kbl < 4; ++kbl, ++hs) {
+                mbar_wait_dl(tile_ready, hs & 1, false);
+                const size_t toff = ((size_t)mt * p.O.kblocks + p.o_kb0 + nb * 4 + kbl) * IMG_TILE_ELEMS;
+                ptx::bulk_s2g(p.O.hi + toff, tile, 16384);
+                ptx::bulk_s2g(p.O.lo + toff, tile + 16384, 16384);
+                ptx::bulk_commit();
+                ptx::bulk_wait_read_all();            // the copies have read the staging tile: hand it back
+                ptx::mbar_arrive(tile_free);
+                ptx::bulk_wait_all();                 // ... and now they are in memory: publish the k-block
+                __threadfence_block();
+                *seq_done = *seq_done + 1;
+              }
+            } else {
+              mbar_wait_dl(tile_ready, hs & 1, false);   // all epilogue warps finished (and fenced) a staged tile
+              ++hs;
+              __threadfence_block();
+              *seq_done = *seq_done + 4;
+              ptx::mbar_arrive(tile_free);
+            }
+          }
+        }
+      }
+    }
   } else {
     // ---------------------------------------------------------------- epilogue (8 warps per CTA, own 128 rows)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const bool elected = warp == 2 && lane == 0;   // issues the bulk stores and publishes seq_done
     uint8_t* tile = smem + Cfg::OFF_STG;            // streamed path: [hi 16 KB | lo 16 KB] of one output k-block
     float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (warp - 2) * Cfg::STG_WARP);   // staged path: per-warp 4 KB
     uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
     const int r_in = q * 32 + lane;
-    uint32_t tl = 0, pending = 0;                   // pending: k-blocks whose bulk stores the elected thread has in flight
-    auto publish_pending = [&]() {                  // elected thread only
-      if (pending) {
-        ptx::bulk_wait_all();
-        __threadfence_block();
-        *seq_done = *seq_done + pending;
-        pending = 0;
-      }
-    };
+    uint32_t tl = 0, hs = 0;                        // hs: hand-overs of the staging memory to the store warp so far
     for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
       const int mt = 2 * ct + (int)rank;
       for (int o = 0; o < c.n_ops; ++o) {
@@ -910,8 +943,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
               uint4 h[4], l[4];
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) ptx::split8_bf16(&acc[cc * 8], h[cc], l[cc]);
-              if (elected) publish_pending();       // the staging tile's previous bulk stores are complete
-              epi_bar();                            // ... and everybody knows it
+              mbar_wait_dl(tile_free, (hs & 1) ^ 1, false);   // the previous contents have been read by the store warp's copies
+              ++hs;
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) {
                 const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);
@@ -919,21 +952,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
                 *reinterpret_cast<uint4*>(tile + 16384 + off) = l[cc];
               }
               ptx::fence_proxy_async_smem();
-              epi_bar();
-              if (elected) {
-                const size_t toff = ((size_t)mt * p.O.kblocks + p.o_kb0 + nb * 4 + kbl) * IMG_TILE_ELEMS;
-                ptx::bulk_s2g(p.O.hi + toff, tile, 16384);
-                ptx::bulk_s2g(p.O.lo + toff, tile + 16384, 16384);
-                ptx::bulk_commit();
-                pending = 1;
-              }
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(tile_ready);
             }
-            // the tile's last k-block must be published NOW: the next op's MMAs (whose accumulator the epilogue
-            // waits for next) need it as an operand
-            if (elected) publish_pending();
           } else {
-            if (elected) publish_pending();         // the per-warp staging areas alias the streamed tile
-            epi_bar();
+            mbar_wait_dl(tile_free, (hs & 1) ^ 1, false);     // the per-warp staging areas alias the streamed tile
+            ++hs;
             if (p.norm != NORM_NONE)
               epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
             else
@@ -947,14 +971,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
             // generic-proxy global stores of this tile -> visible to the bulk copies of the next op's producer
             __threadfence();
             ptx::fence_proxy_async_all();
-            epi_bar();
-            if (elected) *seq_done = *seq_done + 4;
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tile_ready);       // the store warp publishes the tile's four k-blocks
           }
           if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(43 + tl * 4);
         }
       }
     }
-    if (elected) publish_pending();
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -411,8 +411,10 @@ class PeerCounts:
         return N.LtrPeerGather(self._mc or None, self._peers, self.rank, self.world, e % N.GATHER_SLOTS, e // N.GATHER_SLOTS + 1)
 
     def collect(self) -> torch.Tensor:
-        """Counts of all ranks for the oldest publish not collected yet, int32 [world * n_pairs]; enqueues one
-        tiny kernel on the current stream that waits for the world's flags (no host synchronisation)."""
+        """Device-side consumer: counts of all ranks for the oldest publish not collected yet, int32 CUDA tensor
+        [world * n_pairs]; enqueues one tiny kernel on the current stream that waits for the world's flags
+        (no host synchronisation).  Note that it couples the compute stream to the slowest rank; throughput
+        loops should prefer collect_async(), which involves no kernel at all."""
         if self._collected >= self._published:
             raise N.LtrError("PeerCounts.collect(): nothing published")
         e = self._collected
@@ -424,3 +426,55 @@ class PeerCounts:
                                           C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         N.check(rc, "ltr_gather_wait")
         return out
+
+    def collect_async(self) -> "PeerCountsHandle":
+        """Host-side consumer without any kernel: a copy-engine D2H of the oldest uncollected slot (counts + flags)
+        on a side stream, ordered behind everything enqueued on the current stream so far (this rank's own publish).
+        `handle.result()` synchronises that copy only, and re-polls in the (rare) case that a peer's flag had not
+        arrived yet - the compute stream never waits for another rank."""
+        if self._collected >= self._published:
+            raise N.LtrError("PeerCounts.collect_async(): nothing published")
+        e = self._collected
+        self._collected += 1
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream(device=self.device)
+        h = PeerCountsHandle(self, e % N.GATHER_SLOTS, e // N.GATHER_SLOTS + 1)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._side.wait_event(ev)
+        h._enqueue()
+        return h
+
+
+class PeerCountsHandle:
+    def __init__(self, pc: "PeerCounts", slot: int, epoch: int):
+        self.pc, self.slot, self.epoch = pc, slot, epoch
+        W, P = pc.world, pc.n_pairs
+        self._counts = pc.buf[slot * W * P:(slot + 1) * W * P]
+        f0 = N.GATHER_SLOTS * W * P + slot * W
+        self._flags = pc.buf[f0:f0 + W]
+        self._host = torch.empty(W * P + W, dtype=torch.int32).pin_memory()
+        self._done = torch.cuda.Event()
+
+    def _enqueue(self):
+        W, P = self.pc.world, self.pc.n_pairs
+        with torch.cuda.stream(self.pc._side):
+            self._host[W * P:].copy_(self._flags, non_blocking=True)   # flags FIRST: a flag that is set implies its counts are
+            self._host[:W * P].copy_(self._counts, non_blocking=True)  # (the publisher fences between the two)
+            self._done.record(self.pc._side)
+
+    def wait(self):
+        self.result()
+
+    def result(self, timeout_s: float = 30.0) -> torch.Tensor:
+        """-> int32 CPU tensor [world * n_pairs]."""
+        import time
+        W, P = self.pc.world, self.pc.n_pairs
+        t0 = time.perf_counter()
+        while True:
+            self._done.synchronize()
+            if bool((self._host[W * P:] >= self.epoch).all()):
+                return self._host[:W * P]
+            if time.perf_counter() - t0 > timeout_s:
+                raise N.LtrError("PeerCounts: a peer did not publish within the timeout")
+            self._enqueue()

@@ -26,7 +26,7 @@ for multicast in (True, False):
         d1 = torch.from_numpy(np.concatenate([b.T for _, b in pairs], 0).copy()).to(dev)
         out = _ops.match_descriptors(d0, d1, N.LAYOUT_ROWS, P, thr, True, n0=n0, n1=n1, want_dist=False, gather=pc.publish())
         want = gather_counts(out["counts"], P * world)
-        got = pc.collect()
+        got = pc.collect() if step % 2 == 0 else pc.collect_async().result().to(dev)   # device-side / host-side consumer
         torch.cuda.synchronize()
         if not torch.equal(got, want):
             ok = False
