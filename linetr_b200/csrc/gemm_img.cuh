@@ -649,15 +649,16 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
 // Epilogue and op-to-op dependencies.  The trace of the first version (profiles/r2_chain_trace.md) showed the
 // MMA loop at the tensor peak but only 45 % of the launch inside it: at every op boundary the next op waited
 // for the WHOLE epilogue of the previous op's last tile (8-12 k cycles through per-warp staging + LDS + STG)
-// plus a fence and a TMA round trip.  Now image-only tiles are drained k-block-wise and per warp: an epilogue
-// warp owns 32 rows x two whole 64-column k-blocks of the tile; 32 rows x 64 columns of one plane are 4 KB
-// that are CONTIGUOUS in the image tile (four 8-row swizzle atoms), so the warp writes them into its private 4 KB
-// staging area in image layout and lane 0 stores them with one bulk copy (TMA store) - hi plane, then lo plane,
-// no cross-warp hand-over, no LDS / STG phase.  Every warp publishes how many k-blocks it has completed
-// (`warp_done[8]`, after `cp.async.bulk.wait_group 0`); the producer of the NEXT op loads A k-block j as soon
-// as the four warps that produce output k-block j of the previous op have published it - the next op's MMAs
-// start while the previous tile is still being drained.  Tiles with fp32 row outputs / residuals or the row-norm
-// epilogue keep the staged path and publish their k-blocks at the end of the tile.
+// plus a fence and a TMA round trip.  Now image-only tiles are drained in k-block order: all 8 epilogue warps
+// work on the same 64-column k-block, write its hi / lo planes into one 32 KB staging tile in the image's own
+// swizzled layout and a dedicated STORE WARP (warp 10) stores them with two 16 KB bulk copies (TMA store);
+// epilogue and store warp hand the staging tile back and forth through two mbarriers (tile_ready: 8 warp
+// arrivals, tile_free: the bulk copies have read the tile), so no epilogue warp ever waits for a global
+// store to complete.  The store warp also publishes every finished output k-block in the shared sequence
+// counter `seq_done`; the producer of the NEXT op loads A k-block j as soon as output k-block j of the previous
+// op is in memory - the next op's MMAs start while the previous tile is still being drained.  Tiles with fp32
+// row outputs / residuals or the row-norm epilogue keep the per-warp staging path (one hand-over per tile, four
+// k-blocks published at once).
 struct GemmPairCfg {
   static constexpr int BN = 256;
   static constexpr int A_TILE = 16384;
@@ -670,7 +671,7 @@ struct GemmPairCfg {
   static constexpr int OFF_XCH = OFF_BAR + 256;
   static constexpr int SMEM = OFF_XCH + 2048 + 768;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int THREADS = 320;             // TMA warp, MMA / relay warp, 8 epilogue warps
+  static constexpr int THREADS = 352;             // TMA warp, MMA / relay warp, 8 epilogue warps, store warp
 };
 static_assert(GemmPairCfg::SMEM <= 232448, "gemm pair: shared memory budget");
 
@@ -691,7 +692,7 @@ __device__ __forceinline__ void mbar_wait_dl(uint64_t* bar, uint32_t parity, boo
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {
   using Cfg = GemmPairCfg;
   constexpr int BN = Cfg::BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -703,8 +704,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
   uint64_t* empty = peer_full + Cfg::STAGES;      // [3] local, multicast commit
   uint64_t* acc_full = empty + Cfg::STAGES;       // [2] local, multicast commit
   uint64_t* acc_empty = acc_full + 2;             // [2] used in the leader, 16 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  volatile uint32_t* warp_done = tmem_slot + 2;   // [8] per epilogue warp: k-blocks (its 32 rows x 64 columns, both planes) in memory
+  uint64_t* tile_ready = acc_empty + 2;           // [1] local: the 8 epilogue warps filled the staging tile / finished a staged tile
+  uint64_t* tile_free = tile_ready + 1;           // [1] local: the store warp's bulk copies have read the staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_free + 1);
+  volatile uint32_t* seq_done = tmem_slot + 1;    // output k-blocks (64 columns of one m-tile) completed by this CTA's epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -722,7 +725,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
       ptx::mbar_init(&acc_full[b], 1);
       ptx::mbar_init(&acc_empty[b], 16);
     }
-    for (int w = 0; w < 8; ++w) warp_done[w] = 0;
+    ptx::mbar_init(tile_ready, 8);
+    ptx::mbar_init(tile_free, 1);
+    *seq_done = 0;
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -740,7 +745,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs: own A tile, own half of W)
     if (lane == 0) {
-      uint32_t it = 0, tiles_prev = 0, tiles_base = 0;   // tiles_prev: tiles this CTA had finished before the previous op's first tile
+      uint32_t it = 0, seq_prev = 0, seq_base = 0;   // seq_prev: sequence number of the previous op's first output k-block
       for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
         const int mt = 2 * ct + (int)rank;
         for (int o = 0; o < c.n_ops; ++o) {
@@ -751,14 +756,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
           for (int nb = 0; nb < p.n_blks; ++nb)
             for (int kb = 0; kb < nk; ++kb, ++it) {
               if (o > 0 && nb == 0) {
-                // A k-block kb of this op = output k-block kb of the previous op (same m-tile, same CTA): produced by tile
-                // kb / 4 of that op, local k-block kb % 4, i.e. by the four warps (q = 0..3) of column half (kb % 4) / 2,
-                // each of which completes two k-blocks per tile: wait until all four have published it
-                const uint32_t need = 2u * (tiles_prev + (uint32_t)(kb >> 2)) + (uint32_t)(kb & 1) + 1u;
-                const int w0 = ((kb >> 1) & 1) * 4;
-                const long long t0 = clock64();
-                while (warp_done[w0] < need || warp_done[w0 + 1] < need || warp_done[w0 + 2] < need || warp_done[w0 + 3] < need)
-                  if (clock64() - t0 > 4000000000LL) __trap();
+                // A k-block kb of this op = output k-block kb of the previous op (same m-tile, same CTA): wait until
+                // the epilogue has published it (bulk store completed / generic stores fenced)
+                const uint32_t need = seq_prev + (uint32_t)kb + 1;
+                if (*seq_done < need) {
+                  const long long t0 = clock64();
+                  while (*seq_done < need)
+                    if (clock64() - t0 > 4000000000LL) __trap();
+                }
                 __threadfence_block();
                 ptx::fence_proxy_async_all();
                 if (kb == 0 && o < 8) LTR_DBG_STAMP(100 + o);
@@ -775,8 +780,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
               ptx::bulk_g2s(st + 2 * Cfg::A_TILE, whi + woff, Cfg::W_HALF, &full[s]);
               ptx::bulk_g2s(st + 2 * Cfg::A_TILE + Cfg::W_HALF, wlo + woff, Cfg::W_HALF, &full[s]);
             }
-          tiles_prev = tiles_base;
-          tiles_base += (uint32_t)p.n_blks;
+          seq_prev = seq_base;
+          seq_base += 4u * (uint32_t)p.n_blks;
         }
       }
     }
@@ -835,24 +840,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
           }
         }
     }
+  } else if (warp == 10) {
+    // ---------------------------------------------------------------- store warp: staging tile -> global (TMA store), publish
+    if (lane == 0) {
+      uint8_t* tile = smem + Cfg::OFF_STG;
+      uint32_t hs = 0;
+      for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
+        const int mt = 2 * ct + (int)rank;
+        for (int o = 0; o < c.n_ops; ++o) {
+          const GemmImgArgs& p = c.op[o];
+          const bool streamed = p.norm == NORM_NONE && p.O.hi && !p.C && !p.R;
+          for (int nb = 0; nb < p.n_blks; ++nb) {
+            if (streamed) {
+              for (int kbl = 0; kbl < 4; ++kbl, ++hs) {
+                mbar_wait_dl(tile_ready, hs & 1, false);
+                const size_t toff = ((size_t)mt * p.O.kblocks + p.o_kb0 + nb * 4 + kbl) * IMG_TILE_ELEMS;
+                ptx::bulk_s2g(p.O.hi + toff, tile, 16384);
+                ptx::bulk_s2g(p.O.lo + toff, tile + 16384, 16384);
+                ptx::bulk_commit();
+                ptx::bulk_wait_read_all();            // the copies have read the staging tile: hand it back
+                ptx::mbar_arrive(tile_free);
+                ptx::bulk_wait_all();                 // ... and now they are in memory: publish the k-block
+                __threadfence_block();
+                *seq_done = *seq_done + 1;
+              }
+            } else {
+              mbar_wait_dl(tile_ready, hs & 1, false);   // all epilogue warps finished (and fenced) a staged tile
+              ++hs;
+              __threadfence_block();
+              *seq_done = *seq_done + 4;
+              ptx::mbar_arrive(tile_free);
+            }
+          }
+        }
+      }
+    }
   } else {
     // ---------------------------------------------------------------- epilogue (8 warps per CTA, own 128 rows)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int ew = warp - 2;                         // index into warp_done: warps of column half h are 4h .. 4h+3
-    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + ew * Cfg::STG_WARP);   // this warp's private 4 KB
+    uint8_t* tile = smem + Cfg::OFF_STG;            // streamed path: [hi 16 KB | lo 16 KB] of one output k-block
+    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (warp - 2) * Cfg::STG_WARP);   // staged path: per-warp 4 KB
     uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
     const int r_in = q * 32 + lane;
-    uint32_t tl = 0, done = 0, in_flight = 0;        // done: k-blocks published; in_flight: k-blocks whose stores are pending
-    auto publish = [&]() {                           // lane 0 only: previous bulk stores are in memory -> publish them
-      if (in_flight) {
-        ptx::bulk_wait_all();
-        __threadfence_block();
-        done += in_flight;
-        warp_done[ew] = done;
-        in_flight = 0;
-      }
-    };
+    uint32_t tl = 0, hs = 0;                        // hs: hand-overs of the staging memory to the store warp so far
     for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
       const int mt = 2 * ct + (int)rank;
       for (int o = 0; o < c.n_ops; ++o) {
@@ -866,88 +897,67 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
           if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(80 + tl);
           if (streamed) {
 #pragma unroll 1
-            for (int kk = 0; kk < 2; ++kk) {         // this warp's two k-blocks of the tile: local k-block half*2 + kk
-              const int kbl = half * 2 + kk;
-              uint4 h[8], l[8];
-#pragma unroll
-              for (int c32 = 0; c32 < 2; ++c32) {
-                const int c0 = kbl * 64 + c32 * 32, nbase = nb * BN + c0;
-                float acc[32];
-                ptx::tmem_ld32(tacc + (uint32_t)c0, acc);
-                if (kk == 1 && c32 == 1) {           // this warp has read everything it needs from the accumulator
-                  ptx::tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) {
-                    if (leader) ptx::mbar_arrive(&acc_empty[buf]);
-                    else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
-                  }
+            for (int kbl = 0; kbl < 4; ++kbl) {
+              const int c0 = kbl * 64 + half * 32, nbase = nb * BN + c0;
+              float acc[32];
+              ptx::tmem_ld32(tacc + (uint32_t)c0, acc);
+              if (kbl == 3) {   // this warp has read everything it needs from the accumulator
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (leader) ptx::mbar_arrive(&acc_empty[buf]);
+                  else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
                 }
-                if (p.bias) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(p.bias + nbase + j);
-                    acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
-                  }
-                }
-                if (p.act == ACT_RELU) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
-                } else if (p.act == ACT_GELU) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
-                }
-                if (p.Rimg.hi) {   // residual straight from the split-bf16 image (own row, 4 x 16 B per plane)
-                  const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
-                  const uint8_t* rhi = reinterpret_cast<const uint8_t*>(p.Rimg.hi + rtoff);
-                  const uint8_t* rlo = reinterpret_cast<const uint8_t*>(p.Rimg.lo + rtoff);
-#pragma unroll
-                  for (int cc = 0; cc < 4; ++cc) {
-                    const uint32_t off = ptx::sw128_offset(r_in, c32 * 32 + cc * 8);
-                    const uint4 vh = *reinterpret_cast<const uint4*>(rhi + off);
-                    const uint4 vl = *reinterpret_cast<const uint4*>(rlo + off);
-                    const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
-                      acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
-                    }
-                  }
-                }
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) ptx::split8_bf16(&acc[cc * 8], h[c32 * 4 + cc], l[c32 * 4 + cc]);
               }
-              // 32 rows x 64 columns of one plane = 4 KB, contiguous in the image tile (atoms 4q .. 4q+3): stage them in
-              // image layout and store with ONE bulk copy; hi plane, then lo plane through the same 4 KB
-              const size_t toff = ((size_t)mt * p.O.kblocks + p.o_kb0 + nb * 4 + kbl) * IMG_TILE_ELEMS + (size_t)q * 2048;   // bf16 elements
-              if (lane == 0) publish();              // previous k-block's stores complete (also frees the staging area)
-              __syncwarp();
+              if (p.bias) {
 #pragma unroll
-              for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(stgb + ptx::sw128_offset(lane, cc * 8)) = h[cc];
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b = *reinterpret_cast<const float4*>(p.bias + nbase + j);
+                  acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
+                }
+              }
+              if (p.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+              } else if (p.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+              }
+              if (p.Rimg.hi) {   // residual straight from the split-bf16 image (own row, 4 x 16 B per plane)
+                const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
+                const uint8_t* rhi = reinterpret_cast<const uint8_t*>(p.Rimg.hi + rtoff);
+                const uint8_t* rlo = reinterpret_cast<const uint8_t*>(p.Rimg.lo + rtoff);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                  const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);
+                  const uint4 vh = *reinterpret_cast<const uint4*>(rhi + off);
+                  const uint4 vl = *reinterpret_cast<const uint4*>(rlo + off);
+                  const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
+                    acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
+                  }
+                }
+              }
+              uint4 h[4], l[4];
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) ptx::split8_bf16(&acc[cc * 8], h[cc], l[cc]);
+              mbar_wait_dl(tile_free, (hs & 1) ^ 1, false);   // the previous contents have been read by the store warp's copies
+              ++hs;
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);
+                *reinterpret_cast<uint4*>(tile + off) = h[cc];
+                *reinterpret_cast<uint4*>(tile + 16384 + off) = l[cc];
+              }
               ptx::fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) {
-                ptx::bulk_s2g(p.O.hi + toff, stgb, 4096);
-                ptx::bulk_commit();
-                ptx::bulk_wait_read_all();           // the copy has read the staging area
-              }
-              __syncwarp();
-#pragma unroll
-              for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(stgb + ptx::sw128_offset(lane, cc * 8)) = l[cc];
-              ptx::fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                ptx::bulk_s2g(p.O.lo + toff, stgb, 4096);
-                ptx::bulk_commit();
-                in_flight = 1;
-              }
+              if (lane == 0) ptx::mbar_arrive(tile_ready);
             }
-            // the tile's last k-block must be published NOW: the next op's MMAs (whose accumulator this warp waits
-            // for next) need it as an operand
-            if (lane == 0) publish();
-            __syncwarp();
           } else {
-            if (lane == 0) publish();
-            __syncwarp();
+            mbar_wait_dl(tile_free, (hs & 1) ^ 1, false);     // the per-warp staging areas alias the streamed tile
+            ++hs;
             if (p.norm != NORM_NONE)
               epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
             else
@@ -962,10 +972,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) gemm_chain2_
             __threadfence();
             ptx::fence_proxy_async_all();
             __syncwarp();
-            if (lane == 0) {
-              done += 2;                             // a staged tile counts as this warp's two k-blocks
-              warp_done[ew] = done;
-            }
+            if (lane == 0) ptx::mbar_arrive(tile_ready);       // the store warp publishes the tile's four k-blocks
           }
           if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(43 + tl * 4);
         }
