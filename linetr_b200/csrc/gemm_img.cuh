@@ -900,7 +900,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
             for (int kbl = 0; kbl < 4; ++kbl) {
               const int c0 = kbl * 64 + half * 32, nbase = nb * BN + c0;
               float acc[32];
+              const bool fine = tl == 0 && warp == 2 && lane == 0;   // fine-grained trace of the first tile (slots 0..15)
+              if (fine) LTR_DBG_STAMP(kbl * 4);
               ptx::tmem_ld32(tacc + (uint32_t)c0, acc);
+              if (fine) LTR_DBG_STAMP(kbl * 4 + 1);
               if (kbl == 3) {   // this warp has read everything it needs from the accumulator
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -943,8 +946,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
               uint4 h[4], l[4];
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) ptx::split8_bf16(&acc[cc * 8], h[cc], l[cc]);
+              if (fine) LTR_DBG_STAMP(kbl * 4 + 2);
               mbar_wait_dl(tile_free, (hs & 1) ^ 1, false);   // the previous contents have been read by the store warp's copies
               ++hs;
+              if (fine) LTR_DBG_STAMP(kbl * 4 + 3);
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) {
                 const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);

@@ -35,6 +35,11 @@ for tl, nm in enumerate(names):
     af = buf[80 + tl]
     print(f"{nm:20s} acc_empty ok +{a[0]-t0:7d} | first operands +{a[1]-t0:7d} | MMAs committed +{a[2]-t0:7d} | "
           f"epilogue sees acc +{af-t0:7d} | epilogue done +{a[3]-t0:7d}   (mma loop {a[2]-a[1]}, epilogue {a[3]-af})")
+if buf[0]:
+    print("first tile, warp 2, per k-block: [start -> accumulator chunk loaded -> bias/act/split done -> staging tile free]")
+    for k in range(4):
+        a = [buf[k * 4 + i] - t0 for i in range(4)]
+        print(f"  k-block {k}: start +{a[0]}  tmem_ld {a[1] - a[0]}  math {a[2] - a[1]}  wait tile_free {a[3] - a[2]}")
 for d in (1, 2):
     print(f"producer: op boundary {d} passed at +{buf[100 + d] - t0}")
 
