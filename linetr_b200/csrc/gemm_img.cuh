@@ -649,10 +649,8 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
 // Epilogue and op-to-op dependencies.  The trace of the first version (profiles/r2_chain_trace.md) showed the
 // MMA loop at the tensor peak but only 45 % of the launch inside it: at every op boundary the next op waited
 // for the WHOLE epilogue of the previous op's last tile (8-12 k cycles through per-warp staging + LDS + STG)
-// plus a fence and a TMA round trip.  Now image-only tiles are drained in k-block order: SIXTEEN epilogue warps
-// (the bias / activation / 2 x bf16-split work is latency-bound on two warps per scheduler: ~1.1 k cycles per
-// 32-column chunk for ~170 instructions, fine-grained trace in profiles/r2_chain_trace.md; four per scheduler
-// hide it) work on the same 64-column k-block, write its hi / lo planes into one 32 KB staging tile in the image's own
+// plus a fence and a TMA round trip.  Now image-only tiles are drained in k-block order: all 8 epilogue warps
+// work on the same 64-column k-block, write its hi / lo planes into one 32 KB staging tile in the image's own
 // swizzled layout and a dedicated STORE WARP (warp 10) stores them with two 16 KB bulk copies (TMA store);
 // epilogue and store warp hand the staging tile back and forth through two mbarriers (tile_ready: 8 warp
 // arrivals, tile_free: the bulk copies have read the tile), so no epilogue warp ever waits for a global
@@ -673,8 +671,7 @@ struct GemmPairCfg {
   static constexpr int OFF_XCH = OFF_BAR + 256;
   static constexpr int SMEM = OFF_XCH + 2048 + 768;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int EPI_WARPS = 16;            // 4 per TMEM lane quarter: 16 columns of every 64-column k-block each
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32;   // TMA warp, MMA / relay warp, 16 epilogue warps, store warp
+  static constexpr int THREADS = 352;             // TMA warp, MMA / relay warp, 8 epilogue warps, store warp
 };
 static_assert(GemmPairCfg::SMEM <= 232448, "gemm pair: shared memory budget");
 
@@ -695,7 +692,7 @@ __device__ __forceinline__ void mbar_wait_dl(uint64_t* bar, uint32_t parity, boo
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmPairCfg::THREADS, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {
   using Cfg = GemmPairCfg;
   constexpr int BN = Cfg::BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -726,9 +723,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmPairCfg::THREADS
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&acc_full[b], 1);
-      ptx::mbar_init(&acc_empty[b], 2 * Cfg::EPI_WARPS);
+      ptx::mbar_init(&acc_empty[b], 16);
     }
-    ptx::mbar_init(tile_ready, Cfg::EPI_WARPS);
+    ptx::mbar_init(tile_ready, 8);
     ptx::mbar_init(tile_free, 1);
     *seq_done = 0;
     ptx::fence_mbar_init();
@@ -843,7 +840,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmPairCfg::THREADS
           }
         }
     }
-  } else if (warp == 2 + Cfg::EPI_WARPS) {
+  } else if (warp == 10) {
     // ---------------------------------------------------------------- store warp: staging tile -> global (TMA store), publish
     if (lane == 0) {
       uint8_t* tile = smem + Cfg::OFF_STG;
@@ -879,23 +876,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmPairCfg::THREADS
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue (16 warps per CTA, own 128 rows)
-    const int q = warp & 3;                         // TMEM lane quarter
-    const int part = (warp - 2) >> 2;               // streamed tiles: columns 16 part .. 16 part + 16 of every k-block
-    const bool staged_warp = part < 2;              // staged tiles (fp32 rows / row norm) run on warps 2..9 as column halves
+    // ---------------------------------------------------------------- epilogue (8 warps per CTA, own 128 rows)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     uint8_t* tile = smem + Cfg::OFF_STG;            // streamed path: [hi 16 KB | lo 16 KB] of one output k-block
-    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (staged_warp ? warp - 2 : 0) * Cfg::STG_WARP);   // staged path: per-warp 4 KB
+    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (warp - 2) * Cfg::STG_WARP);   // staged path: per-warp 4 KB
     uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
     const int r_in = q * 32 + lane;
     uint32_t tl = 0, hs = 0;                        // hs: hand-overs of the staging memory to the store warp so far
-    auto release_acc = [&](uint32_t buf) {          // this warp needs nothing more from accumulator `buf`
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) ptx::mbar_arrive(&acc_empty[buf]);
-        else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
-      }
-    };
     for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
       const int mt = 2 * ct + (int)rank;
       for (int o = 0; o < c.n_ops; ++o) {
@@ -910,33 +898,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmPairCfg::THREADS
           if (streamed) {
 #pragma unroll 1
             for (int kbl = 0; kbl < 4; ++kbl) {
-              const int c0 = kbl * 64 + part * 16, nbase = nb * BN + c0;
-              float acc[16];
+              const int c0 = kbl * 64 + half * 32, nbase = nb * BN + c0;
+              float acc[32];
               const bool fine = tl == 0 && warp == 2 && lane == 0;   // fine-grained trace of the first tile (slots 0..15)
               if (fine) LTR_DBG_STAMP(kbl * 4);
-              ptx::tmem_ld16(tacc + (uint32_t)c0, acc);
+              ptx::tmem_ld32(tacc + (uint32_t)c0, acc);
               if (fine) LTR_DBG_STAMP(kbl * 4 + 1);
-              if (kbl == 3) release_acc(buf);
+              if (kbl == 3) {   // this warp has read everything it needs from the accumulator
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (leader) ptx::mbar_arrive(&acc_empty[buf]);
+                  else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
+                }
+              }
               if (p.bias) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
+                for (int j = 0; j < 32; j += 4) {
                   const float4 b = *reinterpret_cast<const float4*>(p.bias + nbase + j);
                   acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
                 }
               }
               if (p.act == ACT_RELU) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = fmaxf(acc[j], 0.f);
+                for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
               } else if (p.act == ACT_GELU) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = gelu_erf(acc[j]);
+                for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
               }
-              if (p.Rimg.hi) {   // residual straight from the split-bf16 image (own row, 2 x 16 B per plane)
+              if (p.Rimg.hi) {   // residual straight from the split-bf16 image (own row, 4 x 16 B per plane)
                 const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
                 const uint8_t* rhi = reinterpret_cast<const uint8_t*>(p.Rimg.hi + rtoff);
                 const uint8_t* rlo = reinterpret_cast<const uint8_t*>(p.Rimg.lo + rtoff);
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
+                for (int cc = 0; cc < 4; ++cc) {
                   const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);
                   const uint4 vh = *reinterpret_cast<const uint4*>(rhi + off);
                   const uint4 vl = *reinterpret_cast<const uint4*>(rlo + off);
@@ -948,15 +943,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmPairCfg::THREADS
                   }
                 }
               }
-              uint4 h[2], l[2];
+              uint4 h[4], l[4];
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc) ptx::split8_bf16(&acc[cc * 8], h[cc], l[cc]);
+              for (int cc = 0; cc < 4; ++cc) ptx::split8_bf16(&acc[cc * 8], h[cc], l[cc]);
               if (fine) LTR_DBG_STAMP(kbl * 4 + 2);
               mbar_wait_dl(tile_free, (hs & 1) ^ 1, false);   // the previous contents have been read by the store warp's copies
               ++hs;
               if (fine) LTR_DBG_STAMP(kbl * 4 + 3);
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
+              for (int cc = 0; cc < 4; ++cc) {
                 const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);
                 *reinterpret_cast<uint4*>(tile + off) = h[cc];
                 *reinterpret_cast<uint4*>(tile + 16384 + off) = l[cc];
@@ -968,13 +963,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmPairCfg::THREADS
           } else {
             mbar_wait_dl(tile_free, (hs & 1) ^ 1, false);     // the per-warp staging areas alias the streamed tile
             ++hs;
-            if (staged_warp) {
-              if (p.norm != NORM_NONE)
-                epi_norm_tile(p, tacc, mt, q, part, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
-              else
-                epi_plain_tile<BN>(p, tacc, mt, nb, q, part, lane, stg, stgb);
+            if (p.norm != NORM_NONE)
+              epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
+            else
+              epi_plain_tile<BN>(p, tacc, mt, nb, q, half, lane, stg, stgb);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) ptx::mbar_arrive(&acc_empty[buf]);
+              else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
             }
-            release_acc(buf);
             // generic-proxy global stores of this tile -> visible to the bulk copies of the next op's producer
             __threadfence();
             ptx::fence_proxy_async_all();
