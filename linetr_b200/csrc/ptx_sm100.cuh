@@ -281,10 +281,10 @@ __host__ __device__ constexpr uint32_t sw128_offset(uint32_t row, uint32_t k) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 3) ^ (row & 7u)) & 7u) << 4) + (k & 7u) * 2u;
 }
 
-// fp32 -> bf16 hi (round to nearest) + bf16 lo (truncated residual): x ~= hi + lo to 2^-17 relative
+// fp32 -> bf16 hi + bf16 lo (x ~= hi + lo to ~2^-17 relative)
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
-  lo = __ushort_as_bfloat16((unsigned short)(__float_as_uint(x - __bfloat162float(hi)) >> 16));
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 // 2^x with the SFU approximation (2 ulp; results below 2^-126 flush to zero - softmax weights)
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -292,16 +292,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Two values at once: hi = {bf16_rn(a), bf16_rn(b)} (a in the low half) with the packed conversion
-// (F2FP.BF16.PACK_AB, one instruction per pair), lo = the residuals a - hi_a, b - hi_b TRUNCATED to bf16 with one
-// byte permute (PRMT) - the conversion pipe is a quarter-rate unit and bounded every image-writing epilogue
-// (128 x 256 outputs x 2 planes = 32 k F2FP lanes per GEMM tile, ~1.1 k cycles per 64-column k-block measured);
-// truncating the residual costs nothing on it.  |x - hi - lo| <= 2^-8 |x - hi| <= 2^-17 |x| (hi is round-to-nearest:
-// |x - hi| <= 2^-9 |x|), the same order as the lo*lo term the 3-pass product drops anyway.
+// Two values at once with the packed conversion (F2FP.BF16.PACK_AB: one instruction per pair and no
+// PRMT packing; the scalar form costs two F2F per value): hi = {bf16(a), bf16(b)} (a in the low
+// half), lo = the same of the residuals.  Bit-identical to split_bf16 + pack_bf16.
 __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
   const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
-  lo = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 __device__ __forceinline__ void split8_bf16(const float* v, uint4& hi, uint4& lo) {
   split2_bf16(v[0], v[1], hi.x, lo.x);
