@@ -38,7 +38,10 @@ UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "byte": 1
 
 
 def read_report(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):     # already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {}
