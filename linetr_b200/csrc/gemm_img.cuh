@@ -675,21 +675,17 @@ struct GemmPairCfg {
 };
 static_assert(GemmPairCfg::SMEM <= 232448, "gemm pair: shared memory budget");
 
-// spin with a deadline: a protocol bug must end in a trap (launch failure), not in a hung GPU box
-__device__ __forceinline__ void mbar_wait_dl(uint64_t* bar, uint32_t parity, bool cluster_scope) {
+// spin with a deadline: a protocol bug must end in a trap (launch failure), not in a hung GPU box.
+// NB: plain `mbarrier.try_wait.parity.shared::cta` also for the phases that are completed from the peer CTA
+// (multicast tcgen05.commit, remote arrives) - as CUTLASS' ClusterBarrier does.  An `.acquire.cluster` poll compiles
+// to SYNCS.PHASECHK + CCTL.IVALL, i.e. EVERY poll invalidates the SM's L1: the ncu source view of the first version
+// (profiles/r2_chain_trace.md) had 26 % of all stall samples on that CCTL and the epilogue's bias loads missing L1.
+// Nothing a waiter reads afterwards travels through L1: accumulators come from TMEM (tcgen05.fence), operands are
+// read by the tensor core / TMA through the async proxy.
+__device__ __forceinline__ void mbar_wait_dl(uint64_t* bar, uint32_t parity, bool /*completed_by_peer*/) {
   const long long t0 = clock64();
-  for (;;) {
-    if (cluster_scope) {
-      uint32_t ok;
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok) : "r"(ptx::smem_u32(bar)), "r"(parity) : "memory");
-      if (ok) return;
-    } else if (ptx::mbar_try_wait(bar, parity)) {
-      return;
-    }
+  while (!ptx::mbar_try_wait(bar, parity))
     if (clock64() - t0 > 4000000000LL) __trap();
-  }
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {

@@ -196,9 +196,11 @@ __device__ __forceinline__ uint32_t mapa_shared(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(p)), "r"(rank));
   return a;
 }
-// arrive on an mbarrier that lives in another CTA of the cluster (address from mapa_shared)
+// arrive on an mbarrier that lives in another CTA of the cluster (address from mapa_shared).  Default semantics
+// (as CUTLASS' ClusterBarrier::arrive): an explicit .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR in front of
+// the arrive and made every remote arrival wait for the thread's outstanding global stores.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait with cluster-scope acquire (the phase is completed by arrivals from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
