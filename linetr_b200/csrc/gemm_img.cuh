@@ -840,7 +840,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
     // ---------------------------------------------------------------- store warp: staging tile -> global (TMA store), publish
     if (lane == 0) {
       uint8_t* tile = smem + Cfg::OFF_STG;
-      uint32_t hs = 0;
+      uint32_t hs = 0, unpub = 0;                   // unpub: k-blocks stored but not yet published
       for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
         const int mt = 2 * ct + (int)rank;
         for (int o = 0; o < c.n_ops; ++o) {
@@ -854,11 +854,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
                 ptx::bulk_s2g(p.O.hi + toff, tile, 16384);
                 ptx::bulk_s2g(p.O.lo + toff, tile + 16384, 16384);
                 ptx::bulk_commit();
+                ++unpub;
                 ptx::bulk_wait_read_all();            // the copies have read the staging tile: hand it back
                 ptx::mbar_arrive(tile_free);
-                ptx::bulk_wait_all();                 // ... and now they are in memory: publish the k-block
-                __threadfence_block();
-                *seq_done = *seq_done + 1;
+                // publish what is in memory.  Waiting for THIS k-block's store here would make the store round trip
+                // (~1.2 k cycles, trace) the period of the whole epilogue: let one store stay in flight, except for
+                // the tile's last k-block (the next op needs it before this CTA produces anything else)
+                if (kbl == 3) ptx::bulk_wait_all();
+                else ptx::bulk_wait_but_one();
+                const uint32_t n = kbl == 3 ? unpub : unpub - 1;
+                if (n) {
+                  __threadfence_block();
+                  *seq_done = *seq_done + n;
+                  unpub -= n;
+                }
               }
             } else {
               mbar_wait_dl(tile_ready, hs & 1, false);   // all epilogue warps finished (and fenced) a staged tile
