@@ -8,7 +8,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 KREG='regex:gemm_img|gemm_chain|token_fused|sig_attention|match_tc|match_tail|desc_tiles'
 python bench.py "$@" > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; tail -c 600 $OUT/${TAG}_bench.json
-ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:ltr' -s 22 -c 44 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:gemm_|token_fused|sig_attention|match_|desc_tiles|small_mlp|final_norm|argmin|mutual|segmean|dist_kernel|gather_wait' -s 22 -c 44 --csv \
     --log-file $OUT/${TAG}_launches.csv python bench.py --profile-only --steps 1 --warmup 1 "$@" > /dev/null 2>&1; echo "launch list rc=$?"
 # the .ncu-rep files of 21 launches are ~40 MB each (gpurun_out is capped at 64 MiB): keep the raw-page CSV of both
 # captures (what tools/ncu_summary.py reads) and, as a binary report, only a 4-launch capture with source correlation
