@@ -261,7 +261,30 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(ActImg qkv, ActIm
     const bool live = q0 + row < L;
     float o[32];
     ptx::tmem_ld32(t_o + lane_addr + half * 32, o);
-    if (live) {
+    if (tma) {
+      // aligned 128-line image: this CTA's output (128 rows x 64 head dims) is ONE k-block tile of the output image -
+      // stage hi / lo planes in tile layout (the P operand's memory is dead: the PV MMAs have completed) and store each
+      // with one 16 KB bulk copy instead of eight scattered 16-byte stores per thread
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const float v[8] = {o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv,
+                            o[j + 4] * inv, o[j + 5] * inv, o[j + 6] * inv, o[j + 7] * inv};
+        uint4 hh, ll;
+        ptx::split8_bf16(v, hh, ll);
+        const uint32_t off = ptx::sw128_offset(row, half * 32 + j);
+        *reinterpret_cast<uint4*>(smem + off) = hh;
+        *reinterpret_cast<uint4*>(smem + 16384 + off) = ll;
+      }
+      ptx::fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const size_t toff = ((size_t)(lb >> 7) * out.kblocks + (out_k0 >> 6) + h) * IMG_TILE_ELEMS;
+        ptx::bulk_s2g(out.hi + toff, smem, 16384);
+        ptx::bulk_s2g(out.lo + toff, smem + 16384, 16384);
+        ptx::bulk_commit();
+        ptx::bulk_wait_all();   // in memory before this CTA counts as finished (the next kernel reads it after griddepcontrol.wait)
+      }
+    } else if (live) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         const float v[8] = {o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv,
