@@ -67,7 +67,7 @@ def state_dict_spec(n_desc_layers: int = 1, d_model: int = D_MODEL, d_inner: int
     return spec
 
 
-def make_state_dict(seed: int = 0, n_desc_layers: int = 1) -> dict:
+def make_state_dict(seed: int = 0, n_desc_layers: int = 1, d_inner: int = D_INNER) -> dict:
     """Random-init checkpoint of the LineTR architecture, as {key: np.ndarray}.
 
     Magnitudes are chosen to resemble the shipped checkpoint (weights ~ 1/sqrt(fan_in),
@@ -75,7 +75,7 @@ def make_state_dict(seed: int = 0, n_desc_layers: int = 1) -> dict:
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     sd = {}
-    for key, shape, kind in state_dict_spec(n_desc_layers):
+    for key, shape, kind in state_dict_spec(n_desc_layers, D_MODEL, d_inner):
         if kind == "w":
             fan_in = shape[1]
             v = rng.standard_normal(shape) * (1.0 / np.sqrt(fan_in))

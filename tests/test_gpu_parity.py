@@ -709,3 +709,17 @@ def test_peer_counts_fused_gather_world2():
                           "--master-port", "29577", os.path.join(root, "tools", "peer_counts_check.py")],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, (out.stdout[-3000:], out.stderr[-3000:])
+
+
+@pytest.mark.parametrize("d_inner,L", [(512, 37), (2048, 20), (384, 9)])
+def test_ffn_width_other_than_1024(d_inner, L):
+    """config['d_inner'] != 1024 (the reference accepts any): the FFN hidden image of the workspace is sized by
+    d_inner and the GEMM launcher checks its k-block ranges (a fixed 1024-wide image used to alias tiles
+    silently).  384 is not a multiple of 256: the line stage falls back from the chained engine."""
+    sd = syn.make_state_dict(3, 1, d_inner=d_inner)
+    m = LineTransformer({"mode": "train", "d_inner": d_inner})
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.eval().to(DEV)
+    d = syn.make_image_inputs(900 + d_inner, L, 21, (3, 21))
+    want = orc.line_transformer_forward(sd, d)
+    assert np.abs(fwd(m, d) - want).max() < DESC_TOL_TIGHT

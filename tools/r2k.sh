@@ -1,9 +1,9 @@
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
-timeout 300 python bench.py --no-cpu > gpurun_out/r2s_bench_default.json 2> gpurun_out/r2s_bench.err
+timeout 300 python bench.py --no-cpu > gpurun_out/r2u_bench_default.json 2> gpurun_out/r2u_bench.err
 python - <<PY
 import json
 try:
-    d=json.loads(open("gpurun_out/r2s_bench_default.json").read().strip().splitlines()[-1]); print("default", round(d["value"]), d["ms_per_step"], d["gpu_launches"], {k:(round(v["avg_launch_ms"]*1e3,1), v["launches_per_step"]) for k,v in d["roofline_by_class"].items()})
+    d=json.loads(open("gpurun_out/r2u_bench_default.json").read().strip().splitlines()[-1]); print("default", round(d["value"]), d["ms_per_step"], d["gpu_launches"], {k:(round(v["avg_launch_ms"]*1e3,1), v["launches_per_step"]) for k,v in d["roofline_by_class"].items()})
 except Exception as e:
-    print("default failed", e); print(open("gpurun_out/r2s_bench.err").read()[-600:])
+    print("default failed", e); print(open("gpurun_out/r2u_bench.err").read()[-600:])
 PY
