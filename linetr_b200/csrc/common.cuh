@@ -110,6 +110,9 @@ __device__ int g_dbg_on = 0;
   do {                                                                 \
     if (g_dbg_on && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg_trace[slot] = clock64(); \
   } while (0)
+// host side: trace only the n-th chained GEMM launch after arming (ltr_debug_trace_arm(100 + n)); -1 = no selection
+inline int& dbg_chain_sel() { static int v = -1; return v; }
+inline int& dbg_chain_cnt() { static int v = 0; return v; }
 
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ float warp_sum(float v) {

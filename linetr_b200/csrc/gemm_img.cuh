@@ -35,11 +35,12 @@ struct GemmImgArgs {
   ActImg O; int o_kb0;       // image output (O.hi == nullptr: none); column n -> k-block o_kb0 + n/64
   int M, act;
   // row-normalising epilogue (BN = 256 = N only, one tile spans whole rows):
-  //   NORM_LAYER: y = LayerNorm(acc + bias (+ R)) * ng + nbeta (+ nadd)      (models/line_attention.py:51-53,73-75)
+  //   NORM_LAYER: y = LayerNorm(acc + bias (+ R | Rimg)) * ng + nbeta (+ nadd | NaddImg)      (models/line_attention.py:51-53,73-75)
   //   NORM_L2:    y = (acc + bias) / max(||.||_2, 1e-12)                      (models/line_transformer.py:246)
   int norm; float eps;
   const float* ng; const float* nbeta;
   const float* nadd; int ldadd;   // fp32 rows added AFTER the normalisation or nullptr
+  ActImg NaddImg; int nadd_kb0;   // OR: the same addend read from a split-bf16 image
   int m_tiles, n_blks;
   unsigned long long* trace;   // debug: clock64 stamps of CTA 0 (nullptr = off)
 };
@@ -176,6 +177,43 @@ __device__ __forceinline__ void epi_store_image(const ActImg& O, int kb0, int mt
   __syncwarp();
 }
 
+// acc += X[rows q*32 + lane of m-tile mt][columns nbase .. nbase+32) for a split-bf16 image X (k-block kb0 + nbase/64):
+// coalesced 16-byte chunk loads -> staging -> own row; bf16 -> fp32 is a 16-bit shift
+__device__ __forceinline__ void epi_add_rows_img(const ActImg& X, int kb0, int mt, int nbase, int q, int row0, int M, int lane,
+                                                 uint8_t* stgb, float (&acc)[32]) {
+  const size_t rtoff = ((size_t)mt * X.kblocks + kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
+  const uint8_t* rhi = reinterpret_cast<const uint8_t*>(X.hi + rtoff);
+  const uint8_t* rlo = reinterpret_cast<const uint8_t*>(X.lo + rtoff);
+  const int gch0r = (nbase & 63) >> 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = i * 8 + (lane >> 2), cc = lane & 3;
+    uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+    if (row0 + rl < M) {
+      const uint32_t off = ptx::sw128_offset(q * 32 + rl, (gch0r + cc) * 8);
+      vh = *reinterpret_cast<const uint4*>(rhi + off);
+      vl = *reinterpret_cast<const uint4*>(rlo + off);
+    }
+    const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
+    *reinterpret_cast<uint4*>(stgb + slot) = vh;
+    *reinterpret_cast<uint4*>(stgb + 2048 + slot) = vl;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int slot = (lane * 4 + (cc ^ ((lane >> 1) & 3))) * 16;
+    const uint4 vh = *reinterpret_cast<const uint4*>(stgb + slot);
+    const uint4 vl = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
+    const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
+      acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
+    }
+  }
+  __syncwarp();
+}
+
 // barrier over the 8 epilogue warps only (the TMA and MMA warps never join it)
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -195,6 +233,7 @@ __device__ __forceinline__ void epi_norm_tile(const GemmImgArgs& p, uint32_t tme
       }
     }
     if (p.R) epi_add_rows_f32(p.R, p.ldr, row0, c0, p.M, lane, stg, v);
+    if (p.Rimg.hi) epi_add_rows_img(p.Rimg, p.r_kb0, mt, c0, q, row0, p.M, lane, stgb, v);
   };
   float mean = 0.f, scale;
   if (p.norm == NORM_LAYER) {
@@ -255,6 +294,7 @@ __device__ __forceinline__ void epi_norm_tile(const GemmImgArgs& p, uint32_t tme
       for (int j = 0; j < 32; ++j) v[j] *= scale;
     }
     if (p.nadd) epi_add_rows_f32(p.nadd, p.ldadd, row0, c0, p.M, lane, stg, v);
+    if (p.NaddImg.hi) epi_add_rows_img(p.NaddImg, p.nadd_kb0, mt, c0, q, row0, p.M, lane, stgb, v);
     if (p.C) epi_store_rows_f32(p.C, p.ldc, row0, c0, p.M, lane, stg, v);
     if (p.O.hi) epi_store_image(p.O, p.o_kb0, mt, c0, q, row0, p.M, lane, stgb, v);
   }
@@ -288,40 +328,7 @@ __device__ __forceinline__ void epi_plain_tile(const GemmImgArgs& p, uint32_t tm
       for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
     }
     if (p.R) epi_add_rows_f32(p.R, p.ldr, row0, nbase, p.M, lane, stg, acc);
-    if (p.Rimg.hi) {
-      // residual from a split-bf16 image: coalesced 16-byte chunk loads -> staging -> own row
-      const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
-      const uint8_t* rhi = reinterpret_cast<const uint8_t*>(p.Rimg.hi + rtoff);
-      const uint8_t* rlo = reinterpret_cast<const uint8_t*>(p.Rimg.lo + rtoff);
-      const int gch0r = (nbase & 63) >> 3;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rl = i * 8 + (lane >> 2), cc = lane & 3;
-        uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
-        if (row0 + rl < p.M) {
-          const uint32_t off = ptx::sw128_offset(q * 32 + rl, (gch0r + cc) * 8);
-          vh = *reinterpret_cast<const uint4*>(rhi + off);
-          vl = *reinterpret_cast<const uint4*>(rlo + off);
-        }
-        const int slot = (rl * 4 + (cc ^ ((rl >> 1) & 3))) * 16;
-        *reinterpret_cast<uint4*>(stgb + slot) = vh;
-        *reinterpret_cast<uint4*>(stgb + 2048 + slot) = vl;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int slot = (lane * 4 + (cc ^ ((lane >> 1) & 3))) * 16;
-        const uint4 vh = *reinterpret_cast<const uint4*>(stgb + slot);
-        const uint4 vl = *reinterpret_cast<const uint4*>(stgb + 2048 + slot);
-        const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {   // bf16 -> fp32 is a 16-bit shift
-          acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
-          acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
-        }
-      }
-      __syncwarp();
-    }
+    if (p.Rimg.hi) epi_add_rows_img(p.Rimg, p.r_kb0, mt, nbase, q, row0, p.M, lane, stgb, acc);
     if (p.C) epi_store_rows_f32(p.C, p.ldc, row0, nbase, p.M, lane, stg, acc);
     if (p.O.hi) epi_store_image(p.O, p.o_kb0, mt, nbase, q, row0, p.M, lane, stgb, acc);
   }
@@ -663,11 +670,17 @@ struct GemmPairCfg {
   static constexpr int BN = 256;
   static constexpr int A_TILE = 16384;
   static constexpr int W_HALF = 16384;            // one plane of this CTA's 128 x 64 half of the W tile
-  static constexpr int STAGE = 2 * A_TILE + 2 * W_HALF;
-  static constexpr int STAGES = 3;
-  static constexpr int STG_WARP = 4096;
-  static constexpr int OFF_STG = STAGES * STAGE;
-  static constexpr int OFF_BAR = OFF_STG + 8 * STG_WARP;
+  // Operand ring: FIVE 32 KB slots (hi + lo plane of one tile); k-block `it` takes slot (2 it) % 5 for its half of
+  // W and (2 it + 1) % 5 for its A tile - 2.5 k-blocks in flight.  Three whole 64 KB stages left room for only one
+  // staging tile, and then the hand-over of that tile (all 8 warps written -> two bulk copies issued -> copies have
+  // read the tile -> warps may write again) was 45 % of the epilogue's time (ncu warp-state samples,
+  // profiles/r2_chain_trace.md); the 32 KB taken from the ring pay for a second staging tile.
+  static constexpr int SLOT = 2 * A_TILE;
+  static constexpr int SLOTS = 5;
+  static constexpr int STG_TILE = 2 * A_TILE;     // [hi 16 KB | lo 16 KB] of one 128 x 64 output k-block
+  static constexpr int STG_WARP = 4096;           // staged path: per-warp 4 KB inside the staging tile
+  static constexpr int OFF_STG = SLOTS * SLOT;
+  static constexpr int OFF_BAR = OFF_STG + 2 * STG_TILE;
   static constexpr int OFF_XCH = OFF_BAR + 256;
   static constexpr int SMEM = OFF_XCH + 2048 + 768;
   static constexpr int TMEM_COLS = 512;
@@ -683,10 +696,17 @@ static_assert(GemmPairCfg::SMEM <= 232448, "gemm pair: shared memory budget");
 // Nothing a waiter reads afterwards travels through L1: accumulators come from TMEM (tcgen05.fence), operands are
 // read by the tensor core / TMA through the async proxy.
 __device__ __forceinline__ void mbar_wait_dl(uint64_t* bar, uint32_t parity, bool /*completed_by_peer*/) {
+  if (ptx::mbar_test_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!ptx::mbar_try_wait(bar, parity))
+  // test_wait (pure polling) rather than try_wait: the waiters here are single elected threads or warps with nothing else
+  // to do, and the hardware-suspended form measured ~1 % slower end to end (57.1 k vs 57.7 k pairs/s)
+  while (!ptx::mbar_test_wait(bar, parity))
     if (clock64() - t0 > 4000000000LL) __trap();
 }
+
+// Tiles with an image output and no fp32-row side inputs leave through the streamed epilogue (row norms included; fp32
+// rows C are written straight from registers); anything else takes the per-warp staged path.
+__device__ __forceinline__ bool chain2_streamed(const GemmImgArgs& p) { return p.O.hi && !p.R && !p.nadd; }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {
   using Cfg = GemmPairCfg;
@@ -695,14 +715,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* full = bars;                          // [3] local
-  uint64_t* peer_full = full + Cfg::STAGES;       // [3] used in the leader
-  uint64_t* empty = peer_full + Cfg::STAGES;      // [3] local, multicast commit
-  uint64_t* acc_full = empty + Cfg::STAGES;       // [2] local, multicast commit
+  uint64_t* full = bars;                          // [5] local: this CTA's tile of the slot has landed
+  uint64_t* peer_full = full + Cfg::SLOTS;        // [5] used in the leader: the peer's tile of the slot has landed
+  uint64_t* empty = peer_full + Cfg::SLOTS;       // [5] local, multicast commit: the MMAs reading the slot are complete
+  uint64_t* acc_full = empty + Cfg::SLOTS;        // [2] local, multicast commit
   uint64_t* acc_empty = acc_full + 2;             // [2] used in the leader, 16 arrivals
-  uint64_t* tile_ready = acc_empty + 2;           // [1] local: the 8 epilogue warps filled the staging tile / finished a staged tile
-  uint64_t* tile_free = tile_ready + 1;           // [1] local: the store warp's bulk copies have read the staging tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_free + 1);
+  uint64_t* tile_ready = acc_empty + 2;           // [2] local: the 8 epilogue warps filled staging tile b / finished a staged tile
+  uint64_t* tile_free = tile_ready + 2;           // [2] local: the store warp's bulk copies have read staging tile b
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_free + 2);
   volatile uint32_t* seq_done = tmem_slot + 1;    // output k-blocks (64 columns of one m-tile) completed by this CTA's epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -712,7 +732,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
   const int cl0 = blockIdx.x >> 1, cl_step = gridDim.x >> 1;
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < Cfg::SLOTS; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&peer_full[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -720,9 +740,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&acc_full[b], 1);
       ptx::mbar_init(&acc_empty[b], 16);
+      ptx::mbar_init(&tile_ready[b], 8);
+      ptx::mbar_init(&tile_free[b], 1);
     }
-    ptx::mbar_init(tile_ready, 8);
-    ptx::mbar_init(tile_free, 1);
     *seq_done = 0;
     ptx::fence_mbar_init();
   }
@@ -735,22 +755,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
   ptx::cluster_sync();          // both CTAs' barriers are initialised before any remote arrive / multicast commit
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-  if (tid == 0) LTR_DBG_STAMP(110);
+  // operand slot of ring use u (see GemmPairCfg): W half of k-block it = use 2 it, A tile = use 2 it + 1
+  auto slot_of = [](uint32_t u) { return (int)(u % Cfg::SLOTS); };
+  auto phase_of = [](uint32_t u) { return (u / Cfg::SLOTS) & 1u; };
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs: own A tile, own half of W)
     if (lane == 0) {
+      // this CTA's 128 x 64 half (hi + lo plane) of W k-block kb, n-block nb of op p -> the slot of ring use u
+      auto load_w = [&](const GemmImgArgs& p, int nb, int kb, uint32_t u) {
+        const int sl = slot_of(u);
+        mbar_wait_dl(&empty[sl], phase_of(u) ^ 1, true);
+        uint8_t* st = smem + sl * Cfg::SLOT;
+        const size_t woff = ((size_t)kb * (p.W.N / 8) + (size_t)nb * (BN / 8) + (size_t)rank * 16) * 1024;
+        ptx::mbar_arrive_expect_tx(&full[sl], Cfg::SLOT);
+        ptx::bulk_g2s(st, reinterpret_cast<const uint8_t*>(p.W.hi) + woff, Cfg::W_HALF, &full[sl]);
+        ptx::bulk_g2s(st + Cfg::W_HALF, reinterpret_cast<const uint8_t*>(p.W.lo) + woff, Cfg::W_HALF, &full[sl]);
+      };
+      // The weights do not depend on the kernel in front of this one: the first two k-blocks' W tiles are on their way
+      // before griddepcontrol.wait returns.
+      int pre = 0;
+      if (cl0 < n_ctiles) {
+        const GemmImgArgs& p0 = c.op[0];
+        pre = min(2, p0.W.K / 64);
+        for (int kb = 0; kb < pre; ++kb) load_w(p0, 0, kb, 2u * kb);
+      }
+      pdl_wait();   // A images, residuals: the previous kernel's outputs are complete and visible from here on
+      LTR_DBG_STAMP(110);
       uint32_t it = 0, seq_prev = 0, seq_base = 0;   // seq_prev: sequence number of the previous op's first output k-block
       for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
         const int mt = 2 * ct + (int)rank;
         for (int o = 0; o < c.n_ops; ++o) {
           const GemmImgArgs& p = c.op[o];
           const int nk = p.W.K / 64;
-          const uint8_t* whi = reinterpret_cast<const uint8_t*>(p.W.hi);
-          const uint8_t* wlo = reinterpret_cast<const uint8_t*>(p.W.lo);
           for (int nb = 0; nb < p.n_blks; ++nb)
             for (int kb = 0; kb < nk; ++kb, ++it) {
+              if ((int)it >= pre) load_w(p, nb, kb, 2u * it);
               if (o > 0 && nb == 0) {
                 // A k-block kb of this op = output k-block kb of the previous op (same m-tile, same CTA): wait until
                 // the epilogue has published it (bulk store completed / generic stores fenced)
@@ -764,17 +804,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
                 ptx::fence_proxy_async_all();
                 if (kb == 0 && o < 8) LTR_DBG_STAMP(100 + o);
               }
-              const int s = it % Cfg::STAGES;
-              const uint32_t ph = (it / Cfg::STAGES) & 1;
-              mbar_wait_dl(&empty[s], ph ^ 1, true);
-              uint8_t* st = smem + s * Cfg::STAGE;
+              const uint32_t u = 2u * it + 1u;
+              const int sl = slot_of(u);
+              mbar_wait_dl(&empty[sl], phase_of(u) ^ 1, true);
+              uint8_t* st = smem + sl * Cfg::SLOT;
               const size_t aoff = ((size_t)mt * p.A.kblocks + p.a_kb0 + kb) * IMG_TILE_ELEMS;
-              const size_t woff = ((size_t)kb * (p.W.N / 8) + (size_t)nb * (BN / 8) + (size_t)rank * 16) * 1024;
-              ptx::mbar_arrive_expect_tx(&full[s], Cfg::STAGE);
-              ptx::bulk_g2s(st, p.A.hi + aoff, Cfg::A_TILE, &full[s]);
-              ptx::bulk_g2s(st + Cfg::A_TILE, p.A.lo + aoff, Cfg::A_TILE, &full[s]);
-              ptx::bulk_g2s(st + 2 * Cfg::A_TILE, whi + woff, Cfg::W_HALF, &full[s]);
-              ptx::bulk_g2s(st + 2 * Cfg::A_TILE + Cfg::W_HALF, wlo + woff, Cfg::W_HALF, &full[s]);
+              ptx::mbar_arrive_expect_tx(&full[sl], Cfg::SLOT);
+              ptx::bulk_g2s(st, p.A.hi + aoff, Cfg::A_TILE, &full[sl]);
+              ptx::bulk_g2s(st + Cfg::A_TILE, p.A.lo + aoff, Cfg::A_TILE, &full[sl]);
             }
           seq_prev = seq_base;
           seq_base += 4u * (uint32_t)p.n_blks;
@@ -782,16 +819,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
       }
     }
   } else if (warp == 1) {
+    pdl_wait();
     if (lane == 0 && !leader) {
-      // ---------------------------------------------------------------- peer: relay "my stage landed" to the leader
-      uint32_t it = 0;
+      // ---------------------------------------------------------------- peer: relay "my tile of the slot landed" to the leader
+      uint32_t u = 0;
       for (int ct = cl0; ct < n_ctiles; ct += cl_step)
         for (int o = 0; o < c.n_ops; ++o) {
-          const int n_st = c.op[o].n_blks * (c.op[o].W.K / 64);
-          for (int i = 0; i < n_st; ++i, ++it) {
-            const int s = it % Cfg::STAGES;
-            mbar_wait_dl(&full[s], (it / Cfg::STAGES) & 1, false);
-            ptx::mbar_arrive_cluster(ptx::mapa_shared(&peer_full[s], 0));
+          const int n_use = 2 * c.op[o].n_blks * (c.op[o].W.K / 64);
+          for (int i = 0; i < n_use; ++i, ++u) {
+            const int sl = slot_of(u);
+            mbar_wait_dl(&full[sl], phase_of(u), false);
+            ptx::mbar_arrive_cluster(ptx::mapa_shared(&peer_full[sl], 0));
           }
         }
     } else if (lane == 0) {
@@ -808,15 +846,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
             if (tl < 10) LTR_DBG_STAMP(40 + tl * 4);
             const uint32_t d_tmem = tmem_base + buf * BN;
             for (int kb = 0; kb < nk; ++kb, ++it) {
-              const int s = it % Cfg::STAGES;
-              const uint32_t ph = (it / Cfg::STAGES) & 1;
-              mbar_wait_dl(&full[s], ph, false);
-              mbar_wait_dl(&peer_full[s], ph, true);
+              const uint32_t uw = 2u * it, ua = uw + 1u;
+              const int sw = slot_of(uw), sa = slot_of(ua);
+              mbar_wait_dl(&full[sw], phase_of(uw), false);
+              mbar_wait_dl(&peer_full[sw], phase_of(uw), true);
+              mbar_wait_dl(&full[sa], phase_of(ua), false);
+              mbar_wait_dl(&peer_full[sa], phase_of(ua), true);
               ptx::tc_fence_after();
               if (tl < 10 && kb == 0) LTR_DBG_STAMP(41 + tl * 4);
-              const uint32_t a_hi = ptx::smem_u32(smem + s * Cfg::STAGE);
+              const uint32_t a_hi = ptx::smem_u32(smem + sa * Cfg::SLOT);
               const uint32_t a_lo = a_hi + Cfg::A_TILE;
-              const uint32_t w_hi = a_hi + 2 * Cfg::A_TILE;
+              const uint32_t w_hi = ptx::smem_u32(smem + sw * Cfg::SLOT);
               const uint32_t w_lo = w_hi + Cfg::W_HALF;
 #pragma unroll
               for (int k16 = 0; k16 < 4; ++k16) {
@@ -829,7 +869,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
                 ptx::umma2_bf16(d_tmem, dah, dwl, idesc, 1);
                 ptx::umma2_bf16(d_tmem, dah, dwh, idesc, 1);
               }
-              ptx::umma2_commit(&empty[s], 3);
+              ptx::umma2_commit(&empty[sw], 3);
+              ptx::umma2_commit(&empty[sa], 3);
             }
             ptx::umma2_commit(&acc_full[buf], 3);
             if (tl < 10) LTR_DBG_STAMP(42 + tl * 4);
@@ -837,26 +878,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
         }
     }
   } else if (warp == 10) {
-    // ---------------------------------------------------------------- store warp: staging tile -> global (TMA store), publish
+    pdl_wait();
+    // ---------------------------------------------------------------- store warp: staging tiles -> global (TMA store), publish
     if (lane == 0) {
-      uint8_t* tile = smem + Cfg::OFF_STG;
-      uint32_t hs = 0, unpub = 0;                   // unpub: k-blocks stored but not yet published
+      uint32_t hs = 0, unpub = 0;                   // hs: hand-overs so far; unpub: k-blocks stored but not yet published
       for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
         const int mt = 2 * ct + (int)rank;
         for (int o = 0; o < c.n_ops; ++o) {
           const GemmImgArgs& p = c.op[o];
-          const bool streamed = p.norm == NORM_NONE && p.O.hi && !p.C && !p.R;
+          const bool streamed = chain2_streamed(p);
           for (int nb = 0; nb < p.n_blks; ++nb) {
             if (streamed) {
               for (int kbl = 0; kbl < 4; ++kbl, ++hs) {
-                mbar_wait_dl(tile_ready, hs & 1, false);
+                const uint32_t b = hs & 1, ph = (hs >> 1) & 1;
+                uint8_t* tile = smem + Cfg::OFF_STG + b * Cfg::STG_TILE;
+                mbar_wait_dl(&tile_ready[b], ph, false);
                 const size_t toff = ((size_t)mt * p.O.kblocks + p.o_kb0 + nb * 4 + kbl) * IMG_TILE_ELEMS;
                 ptx::bulk_s2g(p.O.hi + toff, tile, 16384);
                 ptx::bulk_s2g(p.O.lo + toff, tile + 16384, 16384);
                 ptx::bulk_commit();
                 ++unpub;
-                ptx::bulk_wait_read_all();            // the copies have read the staging tile: hand it back
-                ptx::mbar_arrive(tile_free);
+                ptx::bulk_wait_read_all();            // the copies have read staging tile b: hand it back (the epilogue
+                ptx::mbar_arrive(&tile_free[b]);      // is filling the other tile meanwhile)
                 // publish what is in memory.  Waiting for THIS k-block's store here would make the store round trip
                 // (~1.2 k cycles, trace) the period of the whole epilogue: let one store stay in flight, except for
                 // the tile's last k-block (the next op needs it before this CTA produces anything else)
@@ -868,42 +911,154 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
                   *seq_done = *seq_done + n;
                   unpub -= n;
                 }
+                if (hs < 24) LTR_DBG_STAMP(16 + hs);   // trace: hand-over hs processed (published up to here)
               }
             } else {
-              mbar_wait_dl(tile_ready, hs & 1, false);   // all epilogue warps finished (and fenced) a staged tile
+              const uint32_t b = hs & 1, ph = (hs >> 1) & 1;
+              mbar_wait_dl(&tile_ready[b], ph, false);   // all epilogue warps finished (and fenced) a staged tile
               ++hs;
               __threadfence_block();
               *seq_done = *seq_done + 4;
-              ptx::mbar_arrive(tile_free);
+              ptx::mbar_arrive(&tile_free[b]);
             }
           }
         }
       }
     }
   } else {
+    pdl_wait();
     // ---------------------------------------------------------------- epilogue (8 warps per CTA, own 128 rows)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    uint8_t* tile = smem + Cfg::OFF_STG;            // streamed path: [hi 16 KB | lo 16 KB] of one output k-block
-    float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + (warp - 2) * Cfg::STG_WARP);   // staged path: per-warp 4 KB
-    uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
+    // streamed path: staging tile hs & 1 = [hi 16 KB | lo 16 KB] of one output k-block; staged path: per-warp 4 KB in it
+    float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_XCH);
     const int r_in = q * 32 + lane;
     uint32_t tl = 0, hs = 0;                        // hs: hand-overs of the staging memory to the store warp so far
+    // Per-column vectors (bias, LayerNorm gain / shift) of a streamed tile: lane j keeps column j of each of this warp's
+    // four 32-column chunks and the chunk code broadcasts with shuffles.  A broadcast global load per chunk put an L2
+    // round trip (every bias line is touched once per CTA and tile, so it never hits L1) in front of each chunk's
+    // arithmetic: ~1 k cycles per chunk in the clock64 trace against ~350 of issue time (profiles/r2_chain_trace.md).
+    // The bias is fetched one tile ahead.
+    auto col_vec = [&](const float* v, int nb, float (&b)[4]) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) b[k] = v ? v[nb * BN + k * 64 + half * 32 + lane] : 0.f;
+    };
+    auto sel4 = [](const float (&a)[4], int k) { return k == 0 ? a[0] : k == 1 ? a[1] : k == 2 ? a[2] : a[3]; };
+    float bcur[4] = {0.f, 0.f, 0.f, 0.f}, bnxt[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cl0 < n_ctiles) col_vec(c.op[0].bias, 0, bcur);
     for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
       const int mt = 2 * ct + (int)rank;
       for (int o = 0; o < c.n_ops; ++o) {
         const GemmImgArgs& p = c.op[o];
-        const bool streamed = p.norm == NORM_NONE && p.O.hi && !p.C && !p.R;
+        const bool streamed = chain2_streamed(p);
         for (int nb = 0; nb < p.n_blks; ++nb, ++tl) {
           const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+          {   // next tile of this CTA (this op's next n-block, the next op, the next cluster tile)
+            int no = o, nnb = nb + 1;
+            if (nnb == p.n_blks) { nnb = 0; no = o + 1 < c.n_ops ? o + 1 : (ct + cl_step < n_ctiles ? 0 : -1); }
+            if (no >= 0) col_vec(c.op[no].bias, nnb, bnxt);
+          }
+          // Everything the chunk loops need from the op descriptor, in registers: the descriptor sits in the kernel
+          // parameter bank at a dynamic index, and every asm volatile with a memory clobber (tcgen05.ld, mbarrier,
+          // fences) made the compiler re-read its fields - indexed LDC + compare + branch chains were a third of the
+          // warp-state samples inside the chunk arithmetic (ncu source view, profiles/r2_chain_trace.md).
+          const int norm = p.norm, act = p.act;
+          const bool has_bias = p.bias != nullptr;
+          const __nv_bfloat16* res_hi = p.Rimg.hi;
+          const __nv_bfloat16* res_lo = p.Rimg.lo;
+          const size_t res_t0 = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + nb * 4) * IMG_TILE_ELEMS;
+          const __nv_bfloat16* add_hi = p.NaddImg.hi;
+          const __nv_bfloat16* add_lo = p.NaddImg.lo;
+          const size_t add_t0 = ((size_t)mt * p.NaddImg.kblocks + p.nadd_kb0 + nb * 4) * IMG_TILE_ELEMS;
+          float* const crow = (p.C && mt * 128 + r_in < p.M) ? p.C + (long long)(mt * 128 + r_in) * p.ldc + nb * BN : nullptr;
+          const float eps = p.eps;
+          float gk[4] = {1.f, 1.f, 1.f, 1.f}, bek[4] = {0.f, 0.f, 0.f, 0.f};
+          if (streamed && norm == NORM_LAYER) { col_vec(p.ng, 0, gk); col_vec(p.nbeta, 0, bek); }
+          // Side input of a streamed tile from a split-bf16 image (residual, post-norm addend): this thread's own row,
+          // 4 x 16 B per plane and chunk.  Chunk 0 is requested before the accumulator wait, chunk k + 1 right after
+          // chunk k was consumed - an L2 round trip per chunk otherwise (mlp2: 14.5 k cycles per tile against 9 k).
+          uint4 rh[4], rl[4];
+          auto img_load = [&](const __nv_bfloat16* xh, const __nv_bfloat16* xl, size_t toff) {
+            const uint8_t* xhi = reinterpret_cast<const uint8_t*>(xh + toff);
+            const uint8_t* xlo = reinterpret_cast<const uint8_t*>(xl + toff);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const uint32_t off = ptx::sw128_offset(r_in, half * 32 + cc * 8);
+              rh[cc] = *reinterpret_cast<const uint4*>(xhi + off);
+              rl[cc] = *reinterpret_cast<const uint4*>(xlo + off);
+            }
+          };
+          auto img_add = [&](float (&acc)[32]) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const uint32_t wh[4] = {rh[cc].x, rh[cc].y, rh[cc].z, rh[cc].w}, wl[4] = {rl[cc].x, rl[cc].y, rl[cc].z, rl[cc].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
+                acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
+              }
+            }
+          };
+          auto add_bias = [&](float (&acc)[32], int kbl) {
+            const float bk = sel4(bcur, kbl);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += __shfl_sync(0xffffffffu, bk, j);
+          };
+          if (streamed && res_hi) img_load(res_hi, res_lo, res_t0);
           mbar_wait_dl(&acc_full[buf], aph, true);
           ptx::tc_fence_after();
           const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
           if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(80 + tl);
+          if (tl == 2 && lane == 0) LTR_DBG_STAMP(112 + warp - 2);   // trace: per-warp start of the third tile
           if (streamed) {
+            float mean = 0.f, scale = 1.f;
+            if (norm != NORM_NONE) {
+              // ---- row statistics (N == 256: the tile holds whole rows; the two threads of a row exchange partial sums).
+              //      v = acc + bias (+ residual) goes BACK into the accumulator columns (tcgen05.st), so the later passes
+              //      are plain TMEM reads: no second trip to the bias / residual.
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+              for (int kbl = 0; kbl < 4; ++kbl) {
+                const int c0 = kbl * 64 + half * 32;
+                float acc[32];
+                ptx::tmem_ld32(tacc + (uint32_t)c0, acc);
+                if (has_bias) add_bias(acc, kbl);
+                if (res_hi) {
+                  img_add(acc);
+                  if (kbl < 3) img_load(res_hi, res_lo, res_t0 + (size_t)(kbl + 1) * IMG_TILE_ELEMS);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { s1 += acc[j]; s2 = fmaf(acc[j], acc[j], s2); }
+                ptx::tmem_st32(tacc + (uint32_t)c0, acc);
+              }
+              if (add_hi) img_load(add_hi, add_lo, add_t0);   // lands under the exchanges below
+              if (norm == NORM_LAYER) {
+                xch[half * 128 + r_in] = s1;
+                epi_bar();
+                mean = (s1 + xch[(half ^ 1) * 128 + r_in]) * (1.f / 256.f);
+                float ss = 0.f;
+#pragma unroll 1
+                for (int kbl = 0; kbl < 4; ++kbl) {
+                  float acc[32];
+                  ptx::tmem_ld32(tacc + (uint32_t)(kbl * 64 + half * 32), acc);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) { const float d = acc[j] - mean; ss = fmaf(d, d, ss); }
+                }
+                xch[256 + half * 128 + r_in] = ss;
+                epi_bar();
+                ss += xch[256 + (half ^ 1) * 128 + r_in];
+                scale = 1.f / sqrtf(ss * (1.f / 256.f) + eps);
+              } else {
+                float* x = xch + (tl & 1) * 256;   // alternate slots: one barrier per tile is enough
+                x[half * 128 + r_in] = s2;
+                epi_bar();
+                s2 += x[(half ^ 1) * 128 + r_in];
+                scale = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+              }
+            }
 #pragma unroll 1
             for (int kbl = 0; kbl < 4; ++kbl) {
-              const int c0 = kbl * 64 + half * 32, nbase = nb * BN + c0;
+              const int c0 = kbl * 64 + half * 32;
               float acc[32];
               const bool fine = tl == 0 && warp == 2 && lane == 0;   // fine-grained trace of the first tile (slots 0..15)
               if (fine) LTR_DBG_STAMP(kbl * 4);
@@ -917,42 +1072,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
                   else ptx::mbar_arrive_cluster(ptx::mapa_shared(&acc_empty[buf], 0));
                 }
               }
-              if (p.bias) {
+              if (norm == NORM_NONE) {
+                if (has_bias) add_bias(acc, kbl);
+                if (act == ACT_RELU) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 b = *reinterpret_cast<const float4*>(p.bias + nbase + j);
-                  acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
+                  for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+                } else if (act == ACT_GELU) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+                }
+                if (res_hi) {
+                  img_add(acc);
+                  if (kbl < 3) img_load(res_hi, res_lo, res_t0 + (size_t)(kbl + 1) * IMG_TILE_ELEMS);
+                }
+              } else {
+                if (norm == NORM_LAYER) {
+                  const float gg = sel4(gk, kbl), bb = sel4(bek, kbl);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    acc[j] = (acc[j] - mean) * scale * __shfl_sync(0xffffffffu, gg, j) + __shfl_sync(0xffffffffu, bb, j);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) acc[j] *= scale;
+                }
+                if (add_hi) {
+                  img_add(acc);
+                  if (kbl < 3) img_load(add_hi, add_lo, add_t0 + (size_t)(kbl + 1) * IMG_TILE_ELEMS);
                 }
               }
-              if (p.act == ACT_RELU) {
+              if (crow) {   // fp32 rows: this thread's 128 contiguous bytes, four 256-bit stores
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
-              } else if (p.act == ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
-              }
-              if (p.Rimg.hi) {   // residual straight from the split-bf16 image (own row, 4 x 16 B per plane)
-                const size_t rtoff = ((size_t)mt * p.Rimg.kblocks + p.r_kb0 + (nbase >> 6)) * IMG_TILE_ELEMS;
-                const uint8_t* rhi = reinterpret_cast<const uint8_t*>(p.Rimg.hi + rtoff);
-                const uint8_t* rlo = reinterpret_cast<const uint8_t*>(p.Rimg.lo + rtoff);
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                  const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);
-                  const uint4 vh = *reinterpret_cast<const uint4*>(rhi + off);
-                  const uint4 vl = *reinterpret_cast<const uint4*>(rlo + off);
-                  const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    acc[cc * 8 + 2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
-                    acc[cc * 8 + 2 * e + 1] += __uint_as_float(wh[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
-                  }
-                }
+                for (int j = 0; j < 32; j += 8)
+                  ptx::st_global_256(crow + c0 + j, make_uint4(__float_as_uint(acc[j]), __float_as_uint(acc[j + 1]), __float_as_uint(acc[j + 2]), __float_as_uint(acc[j + 3])),
+                                     make_uint4(__float_as_uint(acc[j + 4]), __float_as_uint(acc[j + 5]), __float_as_uint(acc[j + 6]), __float_as_uint(acc[j + 7])));
               }
               uint4 h[4], l[4];
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc) ptx::split8_bf16(&acc[cc * 8], h[cc], l[cc]);
               if (fine) LTR_DBG_STAMP(kbl * 4 + 2);
-              mbar_wait_dl(tile_free, (hs & 1) ^ 1, false);   // the previous contents have been read by the store warp's copies
+              const uint32_t sb = hs & 1;
+              uint8_t* tile = smem + Cfg::OFF_STG + sb * Cfg::STG_TILE;
+              mbar_wait_dl(&tile_free[sb], ((hs >> 1) & 1) ^ 1, false);   // its previous contents have been read by the store warp's copies
               ++hs;
               if (fine) LTR_DBG_STAMP(kbl * 4 + 3);
 #pragma unroll
@@ -963,13 +1123,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
               }
               ptx::fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(tile_ready);
+              if (lane == 0) ptx::mbar_arrive(&tile_ready[sb]);
+              if (tl == 2 && kbl == 0 && lane == 0) LTR_DBG_STAMP(90 + warp - 2);   // trace: per-warp first hand-over of the third tile
             }
           } else {
-            mbar_wait_dl(tile_free, (hs & 1) ^ 1, false);     // the per-warp staging areas alias the streamed tile
+            const uint32_t sb = hs & 1;
+            float* stg = reinterpret_cast<float*>(smem + Cfg::OFF_STG + sb * Cfg::STG_TILE + (warp - 2) * Cfg::STG_WARP);
+            uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
+            mbar_wait_dl(&tile_free[sb], ((hs >> 1) & 1) ^ 1, false);   // the per-warp staging areas alias staging tile sb
             ++hs;
             if (p.norm != NORM_NONE)
-              epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, reinterpret_cast<float*>(smem + Cfg::OFF_XCH));
+              epi_norm_tile(p, tacc, mt, q, half, lane, tl, stg, stgb, xch);
             else
               epi_plain_tile<BN>(p, tacc, mt, nb, q, half, lane, stg, stgb);
             ptx::tc_fence_before();
@@ -982,9 +1146,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
             __threadfence();
             ptx::fence_proxy_async_all();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tile_ready);       // the store warp publishes the tile's four k-blocks
+            if (lane == 0) ptx::mbar_arrive(&tile_ready[sb]);   // the store warp publishes the tile's four k-blocks
           }
           if (tl < 10 && warp == 2 && lane == 0) LTR_DBG_STAMP(43 + tl * 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) bcur[k] = bnxt[k];
         }
       }
     }
@@ -992,6 +1158,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();          // nobody leaves (or frees TMEM) while the peer may still signal / multiply
+  if (tid == 0) LTR_DBG_STAMP(111);
   if (warp == 1) ptx::tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -1037,7 +1204,9 @@ inline int launch_gemm_img(const GemmImgArgs& a, cudaStream_t s, int bn_hint = 0
       return set_error(-1, "gemm_img: residual columns exceed the residual image");
   }
   if (a.norm != NORM_NONE) {
-    if (a.W.N != 256 || a.Rimg.hi || a.act != ACT_NONE || (a.nadd && a.ldadd % 4) || (a.norm == NORM_LAYER && (!a.ng || !a.nbeta)))
+    if (a.W.N != 256 || a.act != ACT_NONE || (a.nadd && a.ldadd % 4) || (a.norm == NORM_LAYER && (!a.ng || !a.nbeta)) ||
+        (a.R && a.Rimg.hi) || (a.nadd && a.NaddImg.hi) ||
+        (a.NaddImg.hi && (a.nadd_kb0 < 0 || a.nadd_kb0 + 4 > a.NaddImg.kblocks)))
       return set_error(-1, "gemm_img: the row-norm epilogue needs N == 256, no activation, fp32 residual");
     return launch_gemm_img_bn<256>(a, s);
   }
@@ -1067,8 +1236,11 @@ inline int launch_gemm_chain(const GemmImgArgs* ops, int n_ops, cudaStream_t s, 
     if (a.a_kb0 < 0 || a.a_kb0 + a.W.K / 64 > a.A.kblocks || (a.O.hi && (a.o_kb0 < 0 || a.o_kb0 + a.W.N / 64 > a.O.kblocks)) ||
         (a.Rimg.hi && (a.r_kb0 < 0 || a.r_kb0 + a.W.N / 64 > a.Rimg.kblocks)))
       return set_error(-1, "gemm_chain: k-block range exceeds an image");
-    if (a.norm != NORM_NONE && (a.W.N != 256 || a.Rimg.hi || a.act != ACT_NONE))
-      return set_error(-1, "gemm_chain: the row-norm epilogue needs N == 256, no activation, fp32 residual");
+    if (a.norm != NORM_NONE && (a.W.N != 256 || a.act != ACT_NONE || (a.norm == NORM_LAYER && (!a.ng || !a.nbeta))))
+      return set_error(-1, "gemm_chain: the row-norm epilogue needs N == 256 and no activation");
+    if ((a.R && a.Rimg.hi) || (a.nadd && a.NaddImg.hi) || ((a.nadd || a.NaddImg.hi) && a.norm == NORM_NONE) ||
+        (a.NaddImg.hi && (a.nadd_kb0 < 0 || a.nadd_kb0 + a.W.N / 64 > a.NaddImg.kblocks)))
+      return set_error(-1, "gemm_chain: residual / addend given twice, addend without a row norm, or its k-blocks exceed the image");
     // op i > 0 reads, k-block for k-block, what op i-1 wrote for the same rows (the kernels' dependency rule)
     if (i > 0 && (a.A.hi != ops[i - 1].O.hi || a.a_kb0 != ops[i - 1].o_kb0 || a.W.K > ops[i - 1].W.N))
       return set_error(-1, "gemm_chain: op i must consume the image op i-1 writes (same k-blocks)");
@@ -1081,7 +1253,11 @@ inline int launch_gemm_chain(const GemmImgArgs* ops, int n_ops, cudaStream_t s, 
     LTR_CUDA_TRY(ensure_dynamic_smem(gemm_chain2_kernel, Cfg::SMEM));
     const int clusters = std::min((c.m_tiles + 1) / 2, device_sm_count() / 2);
     LaunchScope ls(KC_LINEAR, s);
+    const bool traced = dbg_chain_sel() >= 0 && dbg_chain_cnt()++ == dbg_chain_sel();
+    static const int k_on = 1, k_off = 0;
+    if (traced) cudaMemcpyToSymbolAsync(g_dbg_on, &k_on, sizeof(int), 0, cudaMemcpyHostToDevice, s);
     LTR_CUDA_TRY(launch_pdl(gemm_chain2_kernel, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM, s, c));   // __cluster_dims__(2,1,1)
+    if (traced) cudaMemcpyToSymbolAsync(g_dbg_on, &k_off, sizeof(int), 0, cudaMemcpyHostToDevice, s);
     return 0;
   }
   using Cfg = GemmImgCfg<256>;

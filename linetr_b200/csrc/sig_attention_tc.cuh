@@ -282,7 +282,9 @@ __global__ void __launch_bounds__(256) sig_attention_tc_kernel(ActImg qkv, ActIm
         ptx::bulk_s2g(out.hi + toff, smem, 16384);
         ptx::bulk_s2g(out.lo + toff, smem + 16384, 16384);
         ptx::bulk_commit();
-        ptx::bulk_wait_all();   // in memory before this CTA counts as finished (the next kernel reads it after griddepcontrol.wait)
+        // the copies only have to be done READING this CTA's shared memory before it exits; their global writes are
+        // complete (and visible to the next kernel behind griddepcontrol.wait) when the grid is
+        ptx::bulk_wait_read_all();
       }
     } else if (live) {
 #pragma unroll

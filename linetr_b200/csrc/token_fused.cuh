@@ -193,6 +193,17 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int tok0 = (int)((long long)tile * p.lpt * p.T);
+        {
+          // The next tile's descriptors (one contiguous range of rows) start towards L2 now.  All CTAs run their
+          // tiles in the same phase, so without this the whole chip asks HBM for 19 MB in the same few thousand
+          // cycles at the end of L5 and then leaves it idle for the rest of the tile (trace: the last descriptor
+          // group landed 6.1 k cycles after L5's MMAs were complete).
+          const long long nt = (long long)(tile + (int)gridDim.x) * p.lpt * p.T, total = (long long)p.R * p.T;
+          if (nt < total) {
+            const long long rows = min((long long)p.lpt * p.T, total - nt);
+            ptx::bulk_prefetch_l2(p.desc + nt * 256, (uint32_t)(rows * 1024));
+          }
+        }
         ptx::mbar_wait(a_ready, na++ & 1);   // h64
         ptx::tc_fence_after();
         block(1, 0, 0, true);

@@ -1,0 +1,10 @@
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+timeout 300 python bench.py --no-cpu > gpurun_out/r2w_bench_default.json 2> gpurun_out/r2w_bench.err
+python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/r2w_bench_default.json").read().strip().splitlines()[-1]); print("default", round(d["value"]), d["ms_per_step"], d["gpu_launches"], {k:(round(v["avg_launch_ms"]*1e3,1), v["launches_per_step"]) for k,v in d["roofline_by_class"].items()})
+except Exception as e:
+    print("default failed", e); print(open("gpurun_out/r2w_bench.err").read()[-600:])
+PY
+for c in ${TRACE_CHAINS:-3}; do LTR_TRACE_CHAIN=$c timeout 300 python tools/chain_trace.py 2>&1 | grep -v "^sig_attention" | tail -14; done

@@ -1,0 +1,15 @@
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+LTR_CHAIN_MIN_TILES=1 timeout 600 python -m pytest tests -m gpu -q -x -k "forward or varlen or full_size or cfg3 or pair or plumbing or shipped or ffn_width" 2>&1 | tail -3
+timeout 300 python bench.py --no-cpu > gpurun_out/r2x_bench_default.json 2> gpurun_out/r2x_bench.err
+python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/r2x_bench_default.json").read().strip().splitlines()[-1]); print("default", round(d["value"]), d["ms_per_step"], d["gpu_launches"], {k:(round(v["avg_launch_ms"]*1e3,1), v["launches_per_step"]) for k,v in d["roofline_by_class"].items()}, d.get("output_check"))
+except Exception as e:
+    print("default failed", e); print(open("gpurun_out/r2x_bench.err").read()[-600:])
+PY
+for c in ${TRACE_CHAINS:-0 3 7}; do LTR_TRACE_CHAIN=$c timeout 300 python tools/chain_trace.py 2>&1 | grep -v "^sig_attention" | tail -14; done
+if [ -n "${NCU_CHAIN:-}" ]; then
+ncu --set full --clock-control none --import-source on -k regex:gemm_chain2 -s 9 -c 1 -f -o gpurun_out/r2x_chain_src python bench.py --profile-only --steps 1 --warmup 1 > gpurun_out/r2x_ncu_a.log 2>&1; echo "chain ncu rc=$?"
+ncu -i gpurun_out/r2x_chain_src.ncu-rep --page source --csv > gpurun_out/r2x_chain_src.csv 2>/dev/null
+fi
