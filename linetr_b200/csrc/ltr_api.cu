@@ -60,6 +60,7 @@ struct Lin {
 
 struct MlpTail {  // positional encoder: narrow head + the two wide layers (128->256 relu, 256->256)
   SmallMlpWeights head;
+  Lin l2;           // 32 -> 64 as a tensor-core image with K zero-padded to one 64-wide k-block (token stage)
   Lin l3, l4, l5;
 };
 
@@ -159,7 +160,7 @@ static bool fold_layer(const TensorMap& tm, const std::string& conv, const std::
   return true;
 }
 
-struct MlpOffsets { size_t w[3], b[3]; LinOff l3, l4, l5; };
+struct MlpOffsets { size_t w[3], b[3]; LinOff l2, l3, l4, l5; };
 
 static bool pack_pos_encoder(const TensorMap& tm, const std::string& prefix, int in, HostPack& hp, MlpOffsets& off,
                              std::string& err) {
@@ -172,6 +173,12 @@ static bool pack_pos_encoder(const TensorMap& tm, const std::string& prefix, int
     if (l < 3) {
       off.w[l] = hp.add(W);
       off.b[l] = hp.add(b);
+      if (l == 1) {   // 32 -> 64 also as a tensor-core image, K padded to 64
+        std::vector<double> Wp((size_t)64 * 64, 0.0);
+        for (int o = 0; o < 64; ++o)
+          for (int i = 0; i < 32; ++i) Wp[(size_t)o * 64 + i] = W[(size_t)o * 32 + i];
+        off.l2 = hp.add_lin(Wp, b, 64, 64);
+      }
       if (l == 2) off.l3 = hp.add_lin(W, b, ch[l + 1], ch[l]);  // 64 -> 128 also as a tensor-core image
     } else if (l == 3) {
       off.l4 = hp.add_lin(W, b, ch[l + 1], ch[l]);
@@ -186,6 +193,7 @@ static void bind_mlp(MlpTail& m, float* base, uint16_t* tbase, const MlpOffsets&
   m.head.w1 = base + o.w[0]; m.head.b1 = base + o.b[0];
   m.head.w2 = base + o.w[1]; m.head.b2 = base + o.b[1];
   m.head.w3 = base + o.w[2]; m.head.b3 = base + o.b[2];
+  m.l2 = bind_lin(o.l2, base, tbase);
   m.l3 = bind_lin(o.l3, base, tbase);
   m.l4 = bind_lin(o.l4, base, tbase);
   m.l5 = bind_lin(o.l5, base, tbase);
@@ -333,8 +341,8 @@ static int encode_impl(LtrModel* m, const LtrEncodeInput& in, float* out_cf, flo
   {
     TokenFusedArgs a{};
     a.pnt = in.pnt; a.score = in.score; a.desc = in.desc;
-    a.w1 = m->wpe.head.w1; a.b1 = m->wpe.head.b1; a.w2 = m->wpe.head.w2; a.b2 = m->wpe.head.b2;
-    a.W3 = m->wpe.l3.tw; a.W4 = m->wpe.l4.tw; a.W5 = m->wpe.l5.tw;
+    a.w1 = m->wpe.head.w1; a.b1 = m->wpe.head.b1; a.b2 = m->wpe.head.b2;
+    a.W2 = m->wpe.l2.tw; a.W3 = m->wpe.l3.tw; a.W4 = m->wpe.l4.tw; a.W5 = m->wpe.l5.tw;
     a.b3 = m->wpe.l3.b; a.b4 = m->wpe.l4.b; a.b5 = m->wpe.l5.b;
     a.U = m->U; a.s_cls = m->s_cls; a.cls = m->cls;
     a.z = w.z; a.R = R; a.T = T;

@@ -2,8 +2,9 @@
 //
 // One persistent CTA per SM walks tiles of LPT = floor(128 / T) whole lines (LPT*T <= 128 token
 // rows).  Per tile, entirely on chip:
-//   P0  narrow positional MLP 3 -> 32 -> 64 (+ReLU) on CUDA cores            -> h64  (smem, split-bf16)
-//   L3  64 -> 128 (+ReLU)   tcgen05, accumulator in TMEM, epilogue -> smem   -> h128
+//   P0  3 -> 32 (+ReLU) on CUDA cores                                        -> h32  (TMEM, split-bf16)
+//   L2  32 -> 64 (+ReLU)    tcgen05 (N = 64, two K steps)                    -> h64
+//   L3  64 -> 128 (+ReLU)   tcgen05, accumulator in TMEM, epilogue -> TMEM   -> h128
 //   L4  128 -> 256 (+ReLU)  tcgen05                                          -> h256
 //   L5  256 -> 256          tcgen05, epilogue adds the sampled descriptors   -> x = desc + wpe (fp32, smem)
 //   CLS pooling: folded CLS-query scores x.u_h, softmax over the T tokens + CLS per head,
@@ -15,9 +16,23 @@
 // SWIZZLE_128B tensor-map TMA per 32-column block of the tile), the weights (L2 resident, streamed
 // by 1-D TMA through a 2-slot ring) and the pooled z leave/enter the SM.
 //
-// Warp roles: warp 0 = TMA weight producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-9 =
-// 256 worker threads (thread pair per token row: lane = row within the warp's TMEM lane
-// quarter, `half` = which half of the output columns).
+// The activations never touch shared memory: the A operand of every layer lives in TENSOR MEMORY
+// (tcgen05.mma with A from TMEM) as split-bf16 - packed hi pairs and packed lo pairs, written by the
+// previous layer's epilogue with tcgen05.st.  With A in shared memory a 128 x 128 x 16 MMA read
+// 8 KB of operands per 64 cycles - the whole 128 B/clk of the SM's shared memory - while the weight
+// ring and the descriptor stream were writing into the same memory (L5: 9.9 k cycles for 6.1 k of
+// MMAs); and the 128 KB activation image shared its memory with the tile's descriptors, so the last
+// descriptor group could only be fetched after L5 (it landed 6.1 k cycles into the L5 epilogue).
+// Now the 128 KB are the descriptor / x tile alone: the next tile's descriptors are requested the
+// moment the pooling of this tile has read x, and land under the next tile's P0 .. L5.
+// TMEM columns (512): accumulators [0, 256); h128 hi [256, 320) lo [320, 384);
+// h32 hi [256, 272) lo [272, 288); h64 hi [384, 416) lo [416, 448); h256: k < 128 hi [384, 448) lo [448, 512), k >= 128 hi [256, 320)
+// lo [320, 384) - the first half of h256 is written while L4's second n-block still reads h128.
+//
+// Warp roles: warp 0 = TMA weight producer, warp 1 = MMA issuer (+TMEM alloc, descriptor TMA),
+// warps 2-9 = 256 worker threads (thread pair per token row: lane = row within the warp's TMEM lane
+// quarter; the pair splits every 128-column n-block of a layer in halves, so the first n-block's
+// epilogue runs under the second n-block's MMAs).
 #pragma once
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "act_img.cuh"
@@ -31,9 +46,9 @@ struct TokenFusedArgs {
   const float* pnt;    // [R*T, 2]
   const float* score;  // [R*T]
   const float* desc;   // [R*T, 256]
-  // narrow layers (fp32, BN folded): w1 [32,3], w2 [64,32]
-  const float *w1, *b1, *w2, *b2;
-  TcWeight W3, W4, W5;  // [128,64], [256,128], [256,256] packed split-bf16
+  // first layer (fp32, BN folded): w1 [32,3]; b2 [64] is the bias of the second
+  const float *w1, *b1, *b2;
+  TcWeight W2, W3, W4, W5;  // [64,64 (K 32 zero-padded)], [128,64], [256,128], [256,256] packed split-bf16
   const float *b3, *b4, *b5;
   const float* U;      // [4,256] folded CLS query u_h = W_k,h^T q_h / 8 (ltr_create)
   const float* s_cls;  // [4]
@@ -50,8 +65,7 @@ struct TokenFusedSmem {
   static constexpr int OFF_RING = ACT;
   static constexpr int OFF_W1 = OFF_RING + NSLOT * SLOT;   // 96 floats
   static constexpr int OFF_B1 = OFF_W1 + 96 * 4;           // 32
-  static constexpr int OFF_W2 = OFF_B1 + 32 * 4;           // 64*32
-  static constexpr int OFF_B2 = OFF_W2 + 2048 * 4;         // 64
+  static constexpr int OFF_B2 = OFF_B1 + 32 * 4;           // 64
   static constexpr int OFF_B3 = OFF_B2 + 64 * 4;           // 128
   static constexpr int OFF_B4 = OFF_B3 + 128 * 4;          // 256
   static constexpr int OFF_B5 = OFF_B4 + 256 * 4;          // 256
@@ -78,7 +92,6 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
   uint8_t* act = smem;
   float* sW1 = reinterpret_cast<float*>(smem + S::OFF_W1);
   float* sB1 = reinterpret_cast<float*>(smem + S::OFF_B1);
-  float* sW2 = reinterpret_cast<float*>(smem + S::OFF_W2);
   float* sB2 = reinterpret_cast<float*>(smem + S::OFF_B2);
   float* sB3 = reinterpret_cast<float*>(smem + S::OFF_B3);
   float* sB4 = reinterpret_cast<float*>(smem + S::OFF_B4);
@@ -90,18 +103,17 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* full = bars;            // [2] W slot filled (TMA tx)
   uint64_t* empty = bars + 2;       // [2] W slot consumed (tcgen05.commit)
-  uint64_t* a_ready = bars + 4;     // workers -> MMA: A operand image complete (256 arrivals)
-  uint64_t* acc_ready = bars + 5;   // MMA -> workers: accumulator complete (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* a_ready = bars + 4;     // workers -> MMA: A operand complete in tensor memory (256 arrivals)
+  uint64_t* acc_bar = bars + 5;     // [2] MMA -> workers: first / second 128-column n-block of the layer complete (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
   uint64_t* dbar = bars + 8;        // [4] descriptor columns {32 s .. 32 s + 32} u {128 + 32 s ..} of the tile have landed
-  uint64_t* l5_done = bars + 12;    // MMA -> MMA thread: all L5 MMAs complete (last descriptor group may be fetched)
+  uint64_t* x_free = bars + 12;     // workers -> MMA thread: the pooling has read the x tile (256 arrivals)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
 
   for (int i = tid; i < 96; i += blockDim.x) sW1[i] = p.w1[i];
   for (int i = tid; i < 32; i += blockDim.x) sB1[i] = p.b1[i];
-  for (int i = tid; i < 2048; i += blockDim.x) sW2[i] = p.w2[i];
   for (int i = tid; i < 64; i += blockDim.x) sB2[i] = p.b2[i];
   for (int i = tid; i < 128; i += blockDim.x) sB3[i] = p.b3[i];
   for (int i = tid; i < 256; i += blockDim.x) { sB4[i] = p.b4[i]; sB5[i] = p.b5[i]; sCls[i] = p.cls[i]; }
@@ -109,24 +121,28 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     ptx::mbar_init(a_ready, 256);
-    ptx::mbar_init(acc_ready, 1);
+    ptx::mbar_init(&acc_bar[0], 1);
+    ptx::mbar_init(&acc_bar[1], 1);
     for (int i = 0; i < 4; ++i) ptx::mbar_init(&dbar[i], 1);
-    ptx::mbar_init(l5_done, 1);
+    ptx::mbar_init(x_free, 256);
     ptx::prefetch_tensormap(&desc_map);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // tensor-memory columns (see the header)
+  constexpr uint32_t T_H128_HI = 256, T_H128_LO = 320, T_H64_HI = 384, T_H64_LO = 416, T_H32_HI = 256, T_H32_LO = 272;
+  constexpr uint32_t T_H256A_HI = 384, T_H256A_LO = 448, T_H256B_HI = 256, T_H256B_LO = 320;   // A: k < 128, B: k >= 128
   pdl_wait();   // z (output image) may still be read by the previous launch sequence
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- W producer: 13 slots per tile
+    // ---------------------------------------------------------------- W producer: 14 slots per tile
     {
       uint32_t it = 0;
       auto push = [&](const TcWeight& W, int nb, int kb) {
@@ -136,93 +152,82 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
         ptx::mbar_wait(&empty[s], ph ^ 1);
         uint8_t* dst = smem + S::OFF_RING + s * S::SLOT;
         const size_t off = ((size_t)kb * (W.N / 8) + (size_t)nb * 16) * 1024;
-        ptx::mbar_arrive_expect_tx(&full[s], S::SLOT);
-        ptx::bulk_g2s(dst, reinterpret_cast<const uint8_t*>(W.hi) + off, 16384, &full[s]);
-        ptx::bulk_g2s(dst + 16384, reinterpret_cast<const uint8_t*>(W.lo) + off, 16384, &full[s]);
+        const uint32_t bytes = (uint32_t)min(128, W.N - nb * 128) * 128u;   // rows of this n-block x 128 B, per plane
+        ptx::mbar_arrive_expect_tx(&full[s], 2 * bytes);
+        ptx::bulk_g2s(dst, reinterpret_cast<const uint8_t*>(W.hi) + off, bytes, &full[s]);
+        ptx::bulk_g2s(dst + 16384, reinterpret_cast<const uint8_t*>(W.lo) + off, bytes, &full[s]);
         ++it;
       };
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        push(p.W2, 0, 0);
         push(p.W3, 0, 0);
         for (int nb = 0; nb < 2; ++nb)
           for (int kb = 0; kb < 2; ++kb) push(p.W4, nb, kb);
-        for (int kb = 0; kb < 4; ++kb)       // L5: k-block outer (see the MMA issuer: frees the A tiles early)
-          for (int nb = 0; nb < 2; ++nb) push(p.W5, nb, kb);
+        for (int nb = 0; nb < 2; ++nb)
+          for (int kb = 0; kb < 4; ++kb) push(p.W5, nb, kb);
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 128);
-      const uint32_t act_u = ptx::smem_u32(act);
+      constexpr uint32_t idesc128 = ptx::make_idesc_bf16_f32(128, 128), idesc64 = ptx::make_idesc_bf16_f32(128, 64);
       uint32_t it = 0, na = 0;
-      // one [128 x 128 x 64] block: A k-block kb of an activation with nkb k-blocks, W from the ring
-      auto block = [&](int nkb, int kb, int nb, bool first) {
+      // one [128 x 128 x 64] block: K steps k0 .. k0 + 3 (16 wide) of an A operand whose packed hi / lo pairs start at
+      // tensor-memory columns a_hi / a_lo (8 columns per step), W from the ring, accumulator columns nb * 128 ..
+      auto block = [&](uint32_t a_hi, uint32_t a_lo, int nb, bool first, uint32_t idesc, int nk16) {
         const int s = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
-        const uint32_t a_hi = act_u + kb * 16384, a_lo = act_u + (nkb + kb) * 16384;
         const uint32_t w_hi = ptx::smem_u32(smem + S::OFF_RING + s * S::SLOT), w_lo = w_hi + 16384;
         const uint32_t d = tmem_base + nb * 128;
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
+          if (k16 >= nk16) break;
           const uint32_t ko = k16 * 32;
-          const uint64_t dah = ptx::make_sw128_kmajor_desc(a_hi + ko, 1024);
-          const uint64_t dal = ptx::make_sw128_kmajor_desc(a_lo + ko, 1024);
           const uint64_t dwh = ptx::make_sw128_kmajor_desc(w_hi + ko, 1024);
           const uint64_t dwl = ptx::make_sw128_kmajor_desc(w_lo + ko, 1024);
-          ptx::umma_bf16(d, dal, dwh, idesc, !(first && k16 == 0));
-          ptx::umma_bf16(d, dah, dwl, idesc, 1);
-          ptx::umma_bf16(d, dah, dwh, idesc, 1);
+          ptx::umma_bf16_ts(d, tmem_base + a_lo + k16 * 8, dwh, idesc, !(first && k16 == 0));
+          ptx::umma_bf16_ts(d, tmem_base + a_hi + k16 * 8, dwl, idesc, 1);
+          ptx::umma_bf16_ts(d, tmem_base + a_hi + k16 * 8, dwh, idesc, 1);
         }
         ptx::umma_commit(&empty[s]);
         ++it;
       };
       // The tile's sampled descriptors ([128 token rows x 256] fp32 - the one mandatory HBM stream of this stage) land
-      // in the activation region, which holds the L5 A operand (h256) until L5's MMAs have read it.  Column group
-      // s (blocks s and 4 + s of 32 columns) occupies exactly the memory of h256's k-block s (hi and lo tile), so L5
-      // runs k-block outer / n-block inner and group s is fetched as soon as both MMA blocks of k-block s are
-      // complete - which this thread knows without extra barriers: the 2-slot W ring made it wait for them before it
-      // could issue the blocks of k-block s + 1.  Three of the four groups (96 KB) stream in under L5's own MMAs.
+      // in the x tile, four groups of two 32-column SWIZZLE_128B boxes (group s = blocks s and 4 + s, the order the L5
+      // epilogue walks them), requested as soon as the previous tile's pooling has read x.
       float* xs_t = reinterpret_cast<float*>(act);
-      uint32_t nl5 = 0;
-      auto issue_desc = [&](int sgrp, int tok0) {
-        ptx::mbar_arrive_expect_tx(&dbar[sgrp], 2 * 16384);
-        ptx::tma_load_2d(xs_t + sgrp * 4096, &desc_map, sgrp * 32, tok0, &dbar[sgrp]);
-        ptx::tma_load_2d(xs_t + (4 + sgrp) * 4096, &desc_map, (4 + sgrp) * 32, tok0, &dbar[sgrp]);
-      };
+      uint32_t nx = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int tok0 = (int)((long long)tile * p.lpt * p.T);
-        {
-          // The next tile's descriptors (one contiguous range of rows) start towards L2 now.  All CTAs run their
-          // tiles in the same phase, so without this the whole chip asks HBM for 19 MB in the same few thousand
-          // cycles at the end of L5 and then leaves it idle for the rest of the tile (trace: the last descriptor
-          // group landed 6.1 k cycles after L5's MMAs were complete).
-          const long long nt = (long long)(tile + (int)gridDim.x) * p.lpt * p.T, total = (long long)p.R * p.T;
-          if (nt < total) {
-            const long long rows = min((long long)p.lpt * p.T, total - nt);
-            ptx::bulk_prefetch_l2(p.desc + nt * 256, (uint32_t)(rows * 1024));
-          }
+        if (tile != (int)blockIdx.x) ptx::mbar_wait(x_free, nx++ & 1);
+        for (int sgrp = 0; sgrp < 4; ++sgrp) {
+          ptx::mbar_arrive_expect_tx(&dbar[sgrp], 2 * 16384);
+          ptx::tma_load_2d(xs_t + sgrp * 4096, &desc_map, sgrp * 32, tok0, &dbar[sgrp]);
+          ptx::tma_load_2d(xs_t + (4 + sgrp) * 4096, &desc_map, (4 + sgrp) * 32, tok0, &dbar[sgrp]);
         }
+        ptx::mbar_wait(a_ready, na++ & 1);   // h32
+        ptx::tc_fence_after();
+        block(T_H32_HI, T_H32_LO, 0, true, idesc64, 2);   // K = 32: the k-block's upper half is zero padding
+        ptx::umma_commit(&acc_bar[0]);
         ptx::mbar_wait(a_ready, na++ & 1);   // h64
         ptx::tc_fence_after();
-        block(1, 0, 0, true);
-        ptx::umma_commit(acc_ready);
+        block(T_H64_HI, T_H64_LO, 0, true, idesc128, 4);
+        ptx::umma_commit(&acc_bar[0]);
         ptx::mbar_wait(a_ready, na++ & 1);   // h128
         ptx::tc_fence_after();
-        for (int nb = 0; nb < 2; ++nb)
-          for (int kb = 0; kb < 2; ++kb) block(2, kb, nb, kb == 0);
-        ptx::umma_commit(acc_ready);
+        for (int nb = 0; nb < 2; ++nb) {
+          for (int kb = 0; kb < 2; ++kb) block(T_H128_HI + kb * 32, T_H128_LO + kb * 32, nb, kb == 0, idesc128, 4);
+          ptx::umma_commit(&acc_bar[nb]);
+        }
         ptx::mbar_wait(a_ready, na++ & 1);   // h256
         ptx::tc_fence_after();
-        for (int kb = 0; kb < 4; ++kb) {
-          for (int nb = 0; nb < 2; ++nb) block(4, kb, nb, kb == 0);
-          if (kb >= 1) issue_desc(kb - 1, tok0);   // both blocks of k-block kb-1 are complete: their A tiles are dead
+        for (int nb = 0; nb < 2; ++nb) {
+          for (int kb = 0; kb < 4; ++kb)
+            block((kb < 2 ? T_H256A_HI : T_H256B_HI) + (kb & 1) * 32, (kb < 2 ? T_H256A_LO : T_H256B_LO) + (kb & 1) * 32, nb, kb == 0, idesc128, 4);
+          ptx::umma_commit(&acc_bar[nb]);
         }
-        ptx::umma_commit(acc_ready);
-        ptx::umma_commit(l5_done);
-        ptx::mbar_wait(l5_done, nl5++ & 1);
-        issue_desc(3, tok0);
       }
     }
   } else {
@@ -232,20 +237,22 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
     const int r_in = q * 32 + lane;    // token row inside the tile
     const int wt = tid - 64;           // 0..255
     const int rows_used = p.lpt * p.T;
-    uint32_t nacc = 0, dph = 0;   // phase parities: accumulator barrier, descriptor-group barriers
+    uint32_t nacc0 = 0, nacc1 = 0, dph = 0;   // phase parities: the two accumulator barriers, descriptor-group barriers
     auto worker_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    // split-bf16 store of 8 consecutive columns into an activation image with nkb k-blocks
-    auto act_store8 = [&](int nkb, int col, const float (&v)[8]) {
-      uint4 h, l;
-      ptx::split8_bf16(v, h, l);
-      const uint32_t off = (col >> 6) * 16384 + ptx::sw128_offset(r_in, col & 63);
-      *reinterpret_cast<uint4*>(act + off) = h;
-      *reinterpret_cast<uint4*>(act + nkb * 16384 + off) = l;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    // relu(acc + bias) of 32 consecutive columns -> split-bf16 pairs -> 16 + 16 tensor-memory columns of the next
+    // layer's A operand (hi pairs at t_hi, lo pairs at t_lo; the caller passes the column of the first pair)
+    auto act_store32 = [&](const float (&acc)[32], const float* bias, uint32_t t_hi, uint32_t t_lo) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2)
+        ptx::split2_bf16(fmaxf(acc[j] + bias[j], 0.f), fmaxf(acc[j + 1] + bias[j + 1], 0.f), hi[j >> 1], lo[j >> 1]);
+      ptx::tmem_st16(lane_addr + t_hi, hi);
+      ptx::tmem_st16(lane_addr + t_lo, lo);
     };
-    // P0: narrow MLP 3 -> 32 -> 64 (+ReLU) for this thread's token row of tile `t`; the thread produces
-    // outputs [32*half, 32*half+32) and keeps them as packed split-bf16 registers until p0_store().
-    uint32_t p0_hi[16], p0_lo[16];
-    auto p0_compute = [&](int t) {
+    // P0: first layer 3 -> 32 (+ReLU) of this thread's token row; the pair of threads of a row splits the 32 outputs.
+    // Result: 8 + 8 packed split-bf16 pairs -> tensor-memory columns of the h32 operand.
+    auto p0 = [&](int t) {
       const long long tk0 = (long long)t * p.lpt * p.T;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f;
       if (r_in < rows_used && tk0 + r_in < (long long)p.R * p.T) {
@@ -254,124 +261,109 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
         x1 = (p.pnt[2 * tk + 1] - p.cy) / p.scale;
         x2 = p.score[tk];
       }
-      float h1[32];
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int n = 0; n < 32; ++n)
-        h1[n] = fmaxf(fmaf(sW1[n * 3 + 2], x2, fmaf(sW1[n * 3 + 1], x1, fmaf(sW1[n * 3], x0, sB1[n]))), 0.f);
-#pragma unroll
-      for (int n0 = 0; n0 < 32; n0 += 2) {
-        float o[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int n = half * 32 + n0 + j;
-          float a = sB2[n];
-#pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(&sW2[n * 32 + k]);
-            a = fmaf(w.x, h1[k], a); a = fmaf(w.y, h1[k + 1], a);
-            a = fmaf(w.z, h1[k + 2], a); a = fmaf(w.w, h1[k + 3], a);
-          }
-          o[j] = fmaxf(a, 0.f);
-        }
-        ptx::split2_bf16(o[0], o[1], p0_hi[n0 >> 1], p0_lo[n0 >> 1]);
+      for (int j = 0; j < 16; j += 2) {
+        const int n = half * 16 + j;
+        const float a = fmaxf(fmaf(sW1[n * 3 + 2], x2, fmaf(sW1[n * 3 + 1], x1, fmaf(sW1[n * 3], x0, sB1[n]))), 0.f);
+        const float b = fmaxf(fmaf(sW1[n * 3 + 5], x2, fmaf(sW1[n * 3 + 4], x1, fmaf(sW1[n * 3 + 3], x0, sB1[n + 1]))), 0.f);
+        ptx::split2_bf16(a, b, hi[j >> 1], lo[j >> 1]);
       }
-    };
-    auto p0_store = [&]() {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t off = ptx::sw128_offset(r_in, half * 32 + c * 8);
-        *reinterpret_cast<uint4*>(act + off) = make_uint4(p0_hi[c * 4], p0_hi[c * 4 + 1], p0_hi[c * 4 + 2], p0_hi[c * 4 + 3]);
-        *reinterpret_cast<uint4*>(act + 16384 + off) = make_uint4(p0_lo[c * 4], p0_lo[c * 4 + 1], p0_lo[c * 4 + 2], p0_lo[c * 4 + 3]);
-      }
+      ptx::tmem_st8(lane_addr + T_H32_HI + half * 8, hi);
+      ptx::tmem_st8(lane_addr + T_H32_LO + half * 8, lo);
+      ptx::tmem_wait_st();
     };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int line0 = tile * p.lpt;
       const bool tr = (tile == blockIdx.x + gridDim.x) && warp == 2 && lane == 0;   // trace the CTA's 2nd tile
       if (tr) LTR_DBG_STAMP(0);
-      // ---- P0 result of THIS tile (computed during the previous tile's L5 MMAs) -> h64 operand tile
-      if (tile == (int)blockIdx.x) p0_compute(tile);
-      p0_store();
-      ptx::fence_proxy_async_smem();
+      // ---- P0 -> h32 operand
+      p0(tile);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(a_ready);
+      // ---- epilogue L2: 64 columns (32 per thread of the pair) -> h64
+      ptx::mbar_wait(&acc_bar[0], nacc0++ & 1);
+      ptx::tc_fence_after();
+      {
+        float acc[32];
+        ptx::tmem_ld32(lane_addr + (uint32_t)(half * 32), acc);
+        act_store32(acc, sB2 + half * 32, T_H64_HI + half * 16, T_H64_LO + half * 16);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
       ptx::mbar_arrive(a_ready);
       if (tr) LTR_DBG_STAMP(1);
       // ---- epilogue L3: 128 columns (64 per half) -> h128
-      ptx::mbar_wait(acc_ready, nacc++ & 1);
+      ptx::mbar_wait(&acc_bar[0], nacc0++ & 1);
       ptx::tc_fence_after();
       if (tr) LTR_DBG_STAMP(2);
 #pragma unroll 1
       for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         float acc[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = fmaxf(acc[j + e] + sB3[c0 + j + e], 0.f);
-          act_store8(2, c0 + j, o);
-        }
+        ptx::tmem_ld32(lane_addr + (uint32_t)c0, acc);
+        act_store32(acc, sB3 + c0, T_H128_HI + (c0 >> 1), T_H128_LO + (c0 >> 1));
       }
+      ptx::tmem_wait_st();
       ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(a_ready);
       if (tr) LTR_DBG_STAMP(3);
-      // ---- epilogue L4: 256 columns (128 per half) -> h256
-      ptx::mbar_wait(acc_ready, nacc++ & 1);
-      ptx::tc_fence_after();
-      if (tr) LTR_DBG_STAMP(4);
+      // ---- epilogue L4: 256 columns -> h256.  The pair of threads of a row halves EACH 128-column n-block (this
+      //      thread: columns nb * 128 + half * 64 .. + 64), so the first n-block is converted while the second
+      //      is still being multiplied; its pairs go to the h256 columns that do not alias h128 (see the header).
 #pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
-        float acc[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = fmaxf(acc[j + e] + sB4[c0 + j + e], 0.f);
-          act_store8(4, c0 + j, o);
+      for (int nb = 0; nb < 2; ++nb) {
+        if (nb == 0) ptx::mbar_wait(&acc_bar[0], nacc0++ & 1);
+        else ptx::mbar_wait(&acc_bar[1], nacc1++ & 1);
+        ptx::tc_fence_after();
+        if (tr && nb == 0) LTR_DBG_STAMP(4);
+#pragma unroll 1
+        for (int c0 = nb * 128 + half * 64; c0 < nb * 128 + half * 64 + 64; c0 += 32) {
+          float acc[32];
+          ptx::tmem_ld32(lane_addr + (uint32_t)c0, acc);
+          const uint32_t pc = (uint32_t)(c0 & 127) >> 1;   // pair column inside the 64-column half of h256
+          act_store32(acc, sB4 + c0, (nb == 0 ? T_H256A_HI : T_H256B_HI) + pc, (nb == 0 ? T_H256A_LO : T_H256B_LO) + pc);
         }
       }
+      ptx::tmem_wait_st();
       ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(a_ready);
       if (tr) LTR_DBG_STAMP(5);
-      if (tile + (int)gridDim.x < p.n_tiles) p0_compute(tile + gridDim.x);   // overlaps the L5 MMAs
-      // ---- epilogue L5: x = acc + b5 + desc -> fp32 tile in the (now dead) activation region,
-      //      partial CLS scores over this thread's 128 columns
-      ptx::mbar_wait(acc_ready, nacc++ & 1);
-      ptx::tc_fence_after();
-      if (tr) LTR_DBG_STAMP(6);
+      // ---- epilogue L5: x = acc + b5 + desc -> fp32, in place in the x tile (where the TMA put desc);
+      //      partial CLS scores over this thread's 128 columns (64 of each n-block, first n-block first)
       float* xs = reinterpret_cast<float*>(act);
-      // phase A: the tile's descriptors arrive in the (dead) activation region by TMA - eight SWIZZLE_128B
-      // boxes of 32 columns in four groups (group s = column blocks s and 4 + s, one mbarrier per group),
-      // issued by the MMA thread while L5 still runs (see there).  Rows past the end of the batch are
-      // zero-filled by the TMA unit; rows of the next tile that ride along are never used.
-      if (tr) LTR_DBG_STAMP(12);
       float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
 #pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
-        float acc[32];
-        ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-        ptx::mbar_wait(&dbar[(c0 >> 5) & 3], dph);   // this column group of every row has landed
-        if (tr) LTR_DBG_STAMP(13 + ((c0 >> 5) & 3));
+      for (int nb = 0; nb < 2; ++nb) {
+        if (nb == 0) ptx::mbar_wait(&acc_bar[0], nacc0++ & 1);
+        else ptx::mbar_wait(&acc_bar[1], nacc1++ & 1);
+        ptx::tc_fence_after();
+        if (tr && nb == 0) LTR_DBG_STAMP(6);
+        if (tr && nb == 1) LTR_DBG_STAMP(12);
+#pragma unroll 1
+        for (int c0 = nb * 128 + half * 64; c0 < nb * 128 + half * 64 + 64; c0 += 32) {
+          float acc[32];
+          ptx::tmem_ld32(lane_addr + (uint32_t)c0, acc);
+          ptx::mbar_wait(&dbar[(c0 >> 5) & 3], dph);   // this column group of every row has landed (long ago, normally)
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = c0 + j;
-          float4* xp = reinterpret_cast<float4*>(&xs[xs_index(r_in, n)]);
-          const float4 d = *xp;
-          float4 x;
-          x.x = acc[j] + sB5[n] + d.x;
-          x.y = acc[j + 1] + sB5[n + 1] + d.y;
-          x.z = acc[j + 2] + sB5[n + 2] + d.z;
-          x.w = acc[j + 3] + sB5[n + 3] + d.w;
-          *xp = x;
-          const float4 u0 = *reinterpret_cast<const float4*>(&sU[n]);
-          const float4 u1 = *reinterpret_cast<const float4*>(&sU[256 + n]);
-          const float4 u2 = *reinterpret_cast<const float4*>(&sU[512 + n]);
-          const float4 u3 = *reinterpret_cast<const float4*>(&sU[768 + n]);
-          sc0 = fmaf(x.x, u0.x, fmaf(x.y, u0.y, fmaf(x.z, u0.z, fmaf(x.w, u0.w, sc0))));
-          sc1 = fmaf(x.x, u1.x, fmaf(x.y, u1.y, fmaf(x.z, u1.z, fmaf(x.w, u1.w, sc1))));
-          sc2 = fmaf(x.x, u2.x, fmaf(x.y, u2.y, fmaf(x.z, u2.z, fmaf(x.w, u2.w, sc2))));
-          sc3 = fmaf(x.x, u3.x, fmaf(x.y, u3.y, fmaf(x.z, u3.z, fmaf(x.w, u3.w, sc3))));
+          for (int j = 0; j < 32; j += 4) {
+            const int n = c0 + j;
+            float4* xp = reinterpret_cast<float4*>(&xs[xs_index(r_in, n)]);
+            const float4 d = *xp;
+            float4 x;
+            x.x = acc[j] + sB5[n] + d.x;
+            x.y = acc[j + 1] + sB5[n + 1] + d.y;
+            x.z = acc[j + 2] + sB5[n + 2] + d.z;
+            x.w = acc[j + 3] + sB5[n + 3] + d.w;
+            *xp = x;
+            const float4 u0 = *reinterpret_cast<const float4*>(&sU[n]);
+            const float4 u1 = *reinterpret_cast<const float4*>(&sU[256 + n]);
+            const float4 u2 = *reinterpret_cast<const float4*>(&sU[512 + n]);
+            const float4 u3 = *reinterpret_cast<const float4*>(&sU[768 + n]);
+            sc0 = fmaf(x.x, u0.x, fmaf(x.y, u0.y, fmaf(x.z, u0.z, fmaf(x.w, u0.w, sc0))));
+            sc1 = fmaf(x.x, u1.x, fmaf(x.y, u1.y, fmaf(x.z, u1.z, fmaf(x.w, u1.w, sc1))));
+            sc2 = fmaf(x.x, u2.x, fmaf(x.y, u2.y, fmaf(x.z, u2.z, fmaf(x.w, u2.w, sc2))));
+            sc3 = fmaf(x.x, u3.x, fmaf(x.y, u3.y, fmaf(x.z, u3.z, fmaf(x.w, u3.w, sc3))));
+          }
         }
       }
       dph ^= 1;
@@ -446,12 +438,14 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       }
       if (tr) LTR_DBG_STAMP(10);
       worker_sync();   // x tile and probabilities are dead: the next tile may overwrite them
+      ptx::fence_proxy_async_smem();   // this thread's generic accesses to the x tile before the TMA writes that follow
+      ptx::mbar_arrive(x_free);        // -> the MMA thread requests the next tile's descriptors
       if (tr) LTR_DBG_STAMP(11);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda)

@@ -8,8 +8,5 @@ try:
 except Exception as e:
     print("default failed", e); print(open("gpurun_out/r2x_bench.err").read()[-600:])
 PY
-for c in ${TRACE_CHAINS:-0 3 7}; do LTR_TRACE_CHAIN=$c timeout 300 python tools/chain_trace.py 2>&1 | grep -v "^sig_attention" | tail -14; done
-if [ -n "${NCU_CHAIN:-}" ]; then
-ncu --set full --clock-control none --import-source on -k regex:gemm_chain2 -s 9 -c 1 -f -o gpurun_out/r2x_chain_src python bench.py --profile-only --steps 1 --warmup 1 > gpurun_out/r2x_ncu_a.log 2>&1; echo "chain ncu rc=$?"
-ncu -i gpurun_out/r2x_chain_src.ncu-rep --page source --csv > gpurun_out/r2x_chain_src.csv 2>/dev/null
-fi
+for c in ${TRACE_CHAINS:-}; do LTR_TRACE_CHAIN=$c timeout 300 python tools/chain_trace.py 2>&1 | grep -v "^sig_attention" | tail -14; done
+if [ -n "${TOKEN_TRACE:-}" ]; then timeout 300 python tools/token_trace.py 2>&1 | tail -26; fi

@@ -21,8 +21,7 @@ names = ["P0 start", "P0 done", "L3 acc", "ep3 done", "L4 acc", "ep4 done", "L5 
 for i in range(1, 12):
     print(f"{names[i]:14s} +{v[i]-v[i-1]:7d} cycles")
 print("tile total", v[11] - v[0])
-e = [buf[i] for i in range(12, 17)]
-print("ep5 detail (cycles after L5 acc): copies issued", e[0] - v[6], " group landed:", [x - v[6] for x in e[1:]], " ep5 done", v[7] - v[6])
+print("L5 second n-block complete", buf[12] - v[6], "cycles after the first")
 
 an = ["start", "tmem alloc+sync", "kt start", "stage q,k", "stage v^T", "S mma done", "softmax+P stored", "PV mma done", "epilogue done"]
 print("attention CTA (0,0,0), last layer:")
