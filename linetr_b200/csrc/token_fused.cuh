@@ -250,17 +250,29 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       ptx::tmem_st16(lane_addr + t_hi, hi);
       ptx::tmem_st16(lane_addr + t_lo, lo);
     };
+    const float scls0 = p.s_cls[0], scls1 = p.s_cls[1], scls2 = p.s_cls[2], scls3 = p.s_cls[3];
+    // token coordinates + score of this thread's row of tile `t` (raw; requested one tile ahead of their use)
+    float in0 = 0.f, in1 = 0.f, in2 = 0.f;
+    auto p0_fetch = [&](int t) {
+      const long long tk0 = (long long)t * p.lpt * p.T;
+      in0 = in1 = in2 = 0.f;
+      if (t < p.n_tiles && r_in < rows_used && tk0 + r_in < (long long)p.R * p.T) {
+        const long long tk = tk0 + r_in;
+        in0 = p.pnt[2 * tk]; in1 = p.pnt[2 * tk + 1]; in2 = p.score[tk];
+      }
+    };
+    p0_fetch(blockIdx.x);
     // P0: first layer 3 -> 32 (+ReLU) of this thread's token row; the pair of threads of a row splits the 32 outputs.
     // Result: 8 + 8 packed split-bf16 pairs -> tensor-memory columns of the h32 operand.
     auto p0 = [&](int t) {
       const long long tk0 = (long long)t * p.lpt * p.T;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f;
       if (r_in < rows_used && tk0 + r_in < (long long)p.R * p.T) {
-        const long long tk = tk0 + r_in;
-        x0 = (p.pnt[2 * tk] - p.cx) / p.scale;
-        x1 = (p.pnt[2 * tk + 1] - p.cy) / p.scale;
-        x2 = p.score[tk];
+        x0 = (in0 - p.cx) / p.scale;
+        x1 = (in1 - p.cy) / p.scale;
+        x2 = in2;
       }
+      p0_fetch(t + (int)gridDim.x);
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
@@ -372,68 +384,84 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       if (tr) LTR_DBG_STAMP(7);
       worker_sync();
       if (tr) LTR_DBG_STAMP(8);
-      // ---- softmax over the T tokens + CLS of every (line, head), spread over the row threads:
-      //      (1) combine the two column halves of the scores, (2) per (line, head) maximum,
-      //      (3) one exp per (row, head), (4) per (line, head) sum -> 1/sum and the CLS weight.
+      // ---- softmax over the T tokens + CLS of every (line, head).  Thread = (token row, head pair): it scans the
+      //      scores of its row's line (both column halves, 2 x 8 B per token) for the maximum - redundantly per row, which
+      //      costs T cheap iterations instead of a barrier and a pass by 4 * lpt threads - and stores its own exp;
+      //      after one barrier the first row of every line sums the line's exps -> 1/sum and the CLS weight.
       //      sP keeps UNNORMALISED exps; the pooling multiplies by 1/sum once per output.
-      float* sM = sSc + 512;      // [4*lpt] maxima   (second half of the partial-score buffer, dead after (1))
       float* sInv = sP + 512;     // [4*lpt] 1/sum;   sP + 1024 .. : [4*lpt] CLS weight e0
-      if (wt < 128) {
-        const float4 a = *reinterpret_cast<const float4*>(&sSc[wt * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&sSc[(128 + wt) * 4]);
-        *reinterpret_cast<float4*>(&sP[wt * 4]) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      {
+        const int srow = wt & 127, h2 = (wt >> 7) * 2;
+        const bool live = srow < rows_used;
+        const int ln = live ? srow / p.T : 0, rb = ln * p.T;
+        const float c0 = h2 ? scls2 : scls0, c1 = h2 ? scls3 : scls1;
+        float m0 = c0, m1 = c1;
+        if (live) {
+          for (int n = 0; n < p.T; ++n) {
+            const float2 a = *reinterpret_cast<const float2*>(&sSc[(rb + n) * 4 + h2]);
+            const float2 b = *reinterpret_cast<const float2*>(&sSc[(128 + rb + n) * 4 + h2]);
+            m0 = fmaxf(m0, a.x + b.x);
+            m1 = fmaxf(m1, a.y + b.y);
+          }
+          const float2 a = *reinterpret_cast<const float2*>(&sSc[srow * 4 + h2]);
+          const float2 b = *reinterpret_cast<const float2*>(&sSc[(128 + srow) * 4 + h2]);
+          *reinterpret_cast<float2*>(&sP[srow * 4 + h2]) = make_float2(expf(a.x + b.x - m0), expf(a.y + b.y - m1));
+        }
+        worker_sync();
+        if (live && srow == rb) {
+          const float e0 = expf(c0 - m0), e1 = expf(c1 - m1);
+          float s0 = e0, s1 = e1;
+          for (int n = 0; n < p.T; ++n) {
+            const float2 e = *reinterpret_cast<const float2*>(&sP[(rb + n) * 4 + h2]);
+            s0 += e.x;
+            s1 += e.y;
+          }
+          *reinterpret_cast<float2*>(&sInv[ln * 4 + h2]) = make_float2(1.f / s0, 1.f / s1);
+          *reinterpret_cast<float2*>(&sP[1024 + ln * 4 + h2]) = make_float2(e0, e1);
+        }
+        worker_sync();
       }
-      worker_sync();
-      for (int pi = wt; pi < 4 * p.lpt; pi += 256) {
-        const int ln = pi >> 2, h = pi & 3, rb = ln * p.T;
-        float m = p.s_cls[h];
-        for (int n = 0; n < p.T; ++n) m = fmaxf(m, sP[(rb + n) * 4 + h]);
-        sM[pi] = m;
-      }
-      worker_sync();
-      if (wt < rows_used) {
-        const int ln = wt / p.T;
-        float4 v = *reinterpret_cast<const float4*>(&sP[wt * 4]);
-        v.x = expf(v.x - sM[ln * 4 + 0]);
-        v.y = expf(v.y - sM[ln * 4 + 1]);
-        v.z = expf(v.z - sM[ln * 4 + 2]);
-        v.w = expf(v.w - sM[ln * 4 + 3]);
-        *reinterpret_cast<float4*>(&sP[wt * 4]) = v;
-      }
-      worker_sync();
-      for (int pi = wt; pi < 4 * p.lpt; pi += 256) {
-        const int ln = pi >> 2, h = pi & 3, rb = ln * p.T;
-        const float e0 = expf(p.s_cls[h] - sM[pi]);
-        float sum = e0;
-        for (int n = 0; n < p.T; ++n) sum += sP[(rb + n) * 4 + h];
-        sInv[pi] = 1.f / sum;
-        sP[1024 + pi] = e0;
-      }
-      worker_sync();
       if (tr) LTR_DBG_STAMP(9);
       // ---- pooling: z_h[c] = (e0 * cls[c] + sum_n e[n] x[n][c]) / sum.  Thread = (4 channels, 2 of the
       //      4 heads, every second line): one 16-byte x read feeds 8 FMAs (a thread per channel was
-      //      latency-bound at 2 loads per 4 FMAs).  All three indices are warp-uniform except the channels.
+      //      latency-bound at 2 loads per 4 FMAs).  Up to three of the thread's lines run interleaved - 24 independent
+      //      accumulators - so the two loads of a token hide behind the FMAs of the other lines.
       {
         const int cq = wt & 63, lg = (wt >> 6) & 1, hp = wt >> 7;
         const float4 cv = *reinterpret_cast<const float4*>(&sCls[cq * 4]);
-        for (int ln = lg; ln < p.lpt; ln += 2) {
-          const int gl = line0 + ln;
-          if (gl >= p.R) break;
-          const float2 pc = *reinterpret_cast<const float2*>(&sP[1024 + ln * 4 + 2 * hp]);
-          float za0 = pc.x * cv.x, za1 = pc.x * cv.y, za2 = pc.x * cv.z, za3 = pc.x * cv.w;
-          float zb0 = pc.y * cv.x, zb1 = pc.y * cv.y, zb2 = pc.y * cv.z, zb3 = pc.y * cv.w;
-          const int rb = ln * p.T;
-#pragma unroll 3
-          for (int n = 0; n < p.T; ++n) {
-            const float4 xv = *reinterpret_cast<const float4*>(&xs[xs_index(rb + n, cq * 4)]);
-            const float2 pr = *reinterpret_cast<const float2*>(&sP[(rb + n) * 4 + 2 * hp]);
-            za0 = fmaf(pr.x, xv.x, za0); za1 = fmaf(pr.x, xv.y, za1); za2 = fmaf(pr.x, xv.z, za2); za3 = fmaf(pr.x, xv.w, za3);
-            zb0 = fmaf(pr.y, xv.x, zb0); zb1 = fmaf(pr.y, xv.y, zb1); zb2 = fmaf(pr.y, xv.z, zb2); zb3 = fmaf(pr.y, xv.w, zb3);
+        for (int l0 = lg; l0 < p.lpt; l0 += 6) {
+          float za[3][4], zb[3][4];
+          int rb[3];
+          bool ok[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int ln = l0 + 2 * i;
+            ok[i] = ln < p.lpt && line0 + ln < p.R;
+            rb[i] = ok[i] ? ln * p.T : 0;
+            const float2 pc = ok[i] ? *reinterpret_cast<const float2*>(&sP[1024 + ln * 4 + 2 * hp]) : make_float2(0.f, 0.f);
+            za[i][0] = pc.x * cv.x; za[i][1] = pc.x * cv.y; za[i][2] = pc.x * cv.z; za[i][3] = pc.x * cv.w;
+            zb[i][0] = pc.y * cv.x; zb[i][1] = pc.y * cv.y; zb[i][2] = pc.y * cv.z; zb[i][3] = pc.y * cv.w;
           }
-          const float2 iv = *reinterpret_cast<const float2*>(&sInv[ln * 4 + 2 * hp]);
-          img_store4(p.z, gl, (2 * hp) * 256 + cq * 4, za0 * iv.x, za1 * iv.x, za2 * iv.x, za3 * iv.x);
-          img_store4(p.z, gl, (2 * hp + 1) * 256 + cq * 4, zb0 * iv.y, zb1 * iv.y, zb2 * iv.y, zb3 * iv.y);
+#pragma unroll 2
+          for (int n = 0; n < p.T; ++n) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const float4 xv = *reinterpret_cast<const float4*>(&xs[xs_index(rb[i] + n, cq * 4)]);
+              const float2 pr = *reinterpret_cast<const float2*>(&sP[(rb[i] + n) * 4 + 2 * hp]);
+              za[i][0] = fmaf(pr.x, xv.x, za[i][0]); za[i][1] = fmaf(pr.x, xv.y, za[i][1]);
+              za[i][2] = fmaf(pr.x, xv.z, za[i][2]); za[i][3] = fmaf(pr.x, xv.w, za[i][3]);
+              zb[i][0] = fmaf(pr.y, xv.x, zb[i][0]); zb[i][1] = fmaf(pr.y, xv.y, zb[i][1]);
+              zb[i][2] = fmaf(pr.y, xv.z, zb[i][2]); zb[i][3] = fmaf(pr.y, xv.w, zb[i][3]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            if (!ok[i]) continue;
+            const int ln = l0 + 2 * i, gl = line0 + ln;
+            const float2 iv = *reinterpret_cast<const float2*>(&sInv[ln * 4 + 2 * hp]);
+            img_store4(p.z, gl, (2 * hp) * 256 + cq * 4, za[i][0] * iv.x, za[i][1] * iv.x, za[i][2] * iv.x, za[i][3] * iv.x);
+            img_store4(p.z, gl, (2 * hp + 1) * 256 + cq * 4, zb[i][0] * iv.y, zb[i][1] * iv.y, zb[i][2] * iv.y, zb[i][3] * iv.y);
+          }
         }
       }
       if (tr) LTR_DBG_STAMP(10);
