@@ -146,7 +146,6 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
     {
       uint32_t it = 0;
       auto push = [&](const TcWeight& W, int nb, int kb) {
-        if (lane != 0) return;
         const int s = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         ptx::mbar_wait(&empty[s], ph ^ 1);
@@ -158,13 +157,15 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
         ptx::bulk_g2s(dst + 16384, reinterpret_cast<const uint8_t*>(W.lo) + off, bytes, &full[s]);
         ++it;
       };
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        push(p.W2, 0, 0);
-        push(p.W3, 0, 0);
-        for (int nb = 0; nb < 2; ++nb)
-          for (int kb = 0; kb < 2; ++kb) push(p.W4, nb, kb);
-        for (int nb = 0; nb < 2; ++nb)
-          for (int kb = 0; kb < 4; ++kb) push(p.W5, nb, kb);
+      if (lane == 0) {
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+          push(p.W2, 0, 0);
+          push(p.W3, 0, 0);
+          for (int nb = 0; nb < 2; ++nb)
+            for (int kb = 0; kb < 2; ++kb) push(p.W4, nb, kb);
+          for (int nb = 0; nb < 2; ++nb)
+            for (int kb = 0; kb < 4; ++kb) push(p.W5, nb, kb);
+        }
       }
     }
   } else if (warp == 1) {
@@ -194,19 +195,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
         ptx::umma_commit(&empty[s]);
         ++it;
       };
-      // The tile's sampled descriptors ([128 token rows x 256] fp32 - the one mandatory HBM stream of this stage) land
-      // in the x tile, four groups of two 32-column SWIZZLE_128B boxes (group s = blocks s and 4 + s, the order the L5
-      // epilogue walks them), requested as soon as the previous tile's pooling has read x.
-      float* xs_t = reinterpret_cast<float*>(act);
-      uint32_t nx = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int tok0 = (int)((long long)tile * p.lpt * p.T);
-        if (tile != (int)blockIdx.x) ptx::mbar_wait(x_free, nx++ & 1);
-        for (int sgrp = 0; sgrp < 4; ++sgrp) {
-          ptx::mbar_arrive_expect_tx(&dbar[sgrp], 2 * 16384);
-          ptx::tma_load_2d(xs_t + sgrp * 4096, &desc_map, sgrp * 32, tok0, &dbar[sgrp]);
-          ptx::tma_load_2d(xs_t + (4 + sgrp) * 4096, &desc_map, (4 + sgrp) * 32, tok0, &dbar[sgrp]);
-        }
         ptx::mbar_wait(a_ready, na++ & 1);   // h32
         ptx::tc_fence_after();
         block(T_H32_HI, T_H32_LO, 0, true, idesc64, 2);   // K = 32: the k-block's upper half is zero padding
@@ -285,6 +274,101 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       ptx::tmem_st8(lane_addr + T_H32_LO + half * 8, lo);
       ptx::tmem_wait_st();
     };
+    // ---- Softmax and pooling of a tile are DEFERRED into the next tile's MMA phases: they need only shared memory
+    //      (the tile's partial scores and its x tile), while the workers would otherwise idle behind L2, L3, the first
+    //      n-blocks of L4 and L5 (8.8 k of a 26.6 k-cycle tile in the clock64 trace).  The x tile is handed back for the
+    //      next descriptors (x_free) as soon as the last deferred line has been pooled, during L5's first n-block.
+    float* xs = reinterpret_cast<float*>(act);
+    float* sInv = sP + 512;     // [4*lpt] 1/sum;   sP + 1024 .. : [4*lpt] CLS weight e0
+    int prev_line0 = 0;
+    bool have_prev = false;
+    // The tile's sampled descriptors ([128 token rows x 256] fp32 - the one mandatory HBM stream of this stage) land in
+    // the x tile, four groups of two 32-column SWIZZLE_128B boxes (group s = blocks s and 4 + s, the order the L5 epilogue
+    // walks them).  Requested by worker thread 0: for the first tile at once, later the moment all 256 workers have
+    // handed the x tile back (x_free) - a wait its warp has to sit out anyway before it can touch the new descriptors.
+    uint32_t nx = 0;
+    auto request_desc = [&](int t) {
+      float* xs_t = reinterpret_cast<float*>(act);
+      const int tok0 = (int)((long long)t * p.lpt * p.T);
+      for (int sgrp = 0; sgrp < 4; ++sgrp) {
+        ptx::mbar_arrive_expect_tx(&dbar[sgrp], 2 * 16384);
+        ptx::tma_load_2d(xs_t + sgrp * 4096, &desc_map, sgrp * 32, tok0, &dbar[sgrp]);
+        ptx::tma_load_2d(xs_t + (4 + sgrp) * 4096, &desc_map, (4 + sgrp) * 32, tok0, &dbar[sgrp]);
+      }
+    };
+    if (wt == 0 && (int)blockIdx.x < p.n_tiles) request_desc(blockIdx.x);
+    // softmax over the T tokens + CLS of every (line, head).  Thread = (token row, head pair): it scans the scores of
+    // its row's line (both column halves, 2 x 8 B per token) for the maximum - redundantly per row, which costs T
+    // cheap iterations instead of a barrier and a pass by 4 * lpt threads - and stores its own exp; after one barrier
+    // the first row of every line sums the line's exps -> 1/sum and the CLS weight.  sP keeps UNNORMALISED exps; the
+    // pooling multiplies by 1/sum once per output.
+    auto softmax_prev = [&]() {
+      const int srow = wt & 127, h2 = (wt >> 7) * 2;
+      const bool live = srow < rows_used;
+      const int ln = live ? srow / p.T : 0, rb = ln * p.T;
+      const float c0 = h2 ? scls2 : scls0, c1 = h2 ? scls3 : scls1;
+      float m0 = c0, m1 = c1;
+      if (live) {
+        for (int n = 0; n < p.T; ++n) {
+          const float2 a = *reinterpret_cast<const float2*>(&sSc[(rb + n) * 4 + h2]);
+          const float2 b = *reinterpret_cast<const float2*>(&sSc[(128 + rb + n) * 4 + h2]);
+          m0 = fmaxf(m0, a.x + b.x);
+          m1 = fmaxf(m1, a.y + b.y);
+        }
+        const float2 a = *reinterpret_cast<const float2*>(&sSc[srow * 4 + h2]);
+        const float2 b = *reinterpret_cast<const float2*>(&sSc[(128 + srow) * 4 + h2]);
+        *reinterpret_cast<float2*>(&sP[srow * 4 + h2]) = make_float2(expf(a.x + b.x - m0), expf(a.y + b.y - m1));
+      }
+      worker_sync();
+      if (live && srow == rb) {
+        const float e0 = expf(c0 - m0), e1 = expf(c1 - m1);
+        float s0 = e0, s1 = e1;
+        for (int n = 0; n < p.T; ++n) {
+          const float2 e = *reinterpret_cast<const float2*>(&sP[(rb + n) * 4 + h2]);
+          s0 += e.x;
+          s1 += e.y;
+        }
+        *reinterpret_cast<float2*>(&sInv[ln * 4 + h2]) = make_float2(1.f / s0, 1.f / s1);
+        *reinterpret_cast<float2*>(&sP[1024 + ln * 4 + h2]) = make_float2(e0, e1);
+      }
+      worker_sync();
+    };
+    // pooling: z_h[c] = (e0 * cls[c] + sum_n e[n] x[n][c]) / sum.  Thread = (4 channels, every fourth line), all four
+    // heads: one 16-byte x read and one 16-byte read of the four heads' weights feed 16 FMAs, and the x tile is read
+    // ONCE per tile (a head pair per thread read it twice: 256 KB of the SM's shared-memory bandwidth per tile).
+    // Lines [first, first + count) of this thread's line sequence lg, lg + 4, ...
+    auto pool_prev = [&](int first, int count) {
+      const int cq = wt & 63, lg = wt >> 6;
+      const float4 cv = *reinterpret_cast<const float4*>(&sCls[cq * 4]);
+      for (int k = first; k < first + count; ++k) {
+        const int ln = lg + 4 * k;
+        if (ln >= p.lpt) break;
+        const int gl = prev_line0 + ln;
+        if (gl >= p.R) break;
+        const float4 pc = *reinterpret_cast<const float4*>(&sP[1024 + ln * 4]);
+        float z[4][4];
+        const float pcv[4] = {pc.x, pc.y, pc.z, pc.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { z[h][0] = pcv[h] * cv.x; z[h][1] = pcv[h] * cv.y; z[h][2] = pcv[h] * cv.z; z[h][3] = pcv[h] * cv.w; }
+        const int rb = ln * p.T;
+#pragma unroll 3
+        for (int n = 0; n < p.T; ++n) {
+          const float4 xv = *reinterpret_cast<const float4*>(&xs[xs_index(rb + n, cq * 4)]);
+          const float4 pr = *reinterpret_cast<const float4*>(&sP[(rb + n) * 4]);
+          const float prv[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            z[h][0] = fmaf(prv[h], xv.x, z[h][0]); z[h][1] = fmaf(prv[h], xv.y, z[h][1]);
+            z[h][2] = fmaf(prv[h], xv.z, z[h][2]); z[h][3] = fmaf(prv[h], xv.w, z[h][3]);
+          }
+        }
+        const float4 iv = *reinterpret_cast<const float4*>(&sInv[ln * 4]);
+        const float ivv[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          img_store4(p.z, gl, h * 256 + cq * 4, z[h][0] * ivv[h], z[h][1] * ivv[h], z[h][2] * ivv[h], z[h][3] * ivv[h]);
+      }
+    };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int line0 = tile * p.lpt;
       const bool tr = (tile == blockIdx.x + gridDim.x) && warp == 2 && lane == 0;   // trace the CTA's 2nd tile
@@ -293,6 +377,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       p0(tile);
       ptx::tc_fence_before();
       ptx::mbar_arrive(a_ready);
+      if (have_prev) softmax_prev();   // under the L2 MMAs
       // ---- epilogue L2: 64 columns (32 per thread of the pair) -> h64
       ptx::mbar_wait(&acc_bar[0], nacc0++ & 1);
       ptx::tc_fence_after();
@@ -305,6 +390,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       ptx::tc_fence_before();
       ptx::mbar_arrive(a_ready);
       if (tr) LTR_DBG_STAMP(1);
+      if (have_prev) pool_prev(0, 1);   // under the L3 MMAs
       // ---- epilogue L3: 128 columns (64 per half) -> h128
       ptx::mbar_wait(&acc_bar[0], nacc0++ & 1);
       ptx::tc_fence_after();
@@ -319,6 +405,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       ptx::tc_fence_before();
       ptx::mbar_arrive(a_ready);
       if (tr) LTR_DBG_STAMP(3);
+      if (have_prev) pool_prev(1, 1);   // under L4's first n-block
       // ---- epilogue L4: 256 columns -> h256.  The pair of threads of a row halves EACH 128-column n-block (this
       //      thread: columns nb * 128 + half * 64 .. + 64), so the first n-block is converted while the second
       //      is still being multiplied; its pairs go to the h256 columns that do not alias h128 (see the header).
@@ -340,9 +427,17 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       ptx::tc_fence_before();
       ptx::mbar_arrive(a_ready);
       if (tr) LTR_DBG_STAMP(5);
+      if (have_prev) {                  // under L5's first n-block: the rest, then the x tile is free for this tile's descriptors
+        pool_prev(2, 1 << 30);
+        ptx::fence_proxy_async_smem();  // this thread's generic accesses to the x tile before the TMA writes that follow
+        ptx::mbar_arrive(x_free);
+        if (wt == 0) {
+          ptx::mbar_wait(x_free, nx++ & 1);
+          request_desc(tile);
+        }
+      }
       // ---- epilogue L5: x = acc + b5 + desc -> fp32, in place in the x tile (where the TMA put desc);
       //      partial CLS scores over this thread's 128 columns (64 of each n-block, first n-block first)
-      float* xs = reinterpret_cast<float*>(act);
       float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
 #pragma unroll 1
       for (int nb = 0; nb < 2; ++nb) {
@@ -384,91 +479,14 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       if (tr) LTR_DBG_STAMP(7);
       worker_sync();
       if (tr) LTR_DBG_STAMP(8);
-      // ---- softmax over the T tokens + CLS of every (line, head).  Thread = (token row, head pair): it scans the
-      //      scores of its row's line (both column halves, 2 x 8 B per token) for the maximum - redundantly per row, which
-      //      costs T cheap iterations instead of a barrier and a pass by 4 * lpt threads - and stores its own exp;
-      //      after one barrier the first row of every line sums the line's exps -> 1/sum and the CLS weight.
-      //      sP keeps UNNORMALISED exps; the pooling multiplies by 1/sum once per output.
-      float* sInv = sP + 512;     // [4*lpt] 1/sum;   sP + 1024 .. : [4*lpt] CLS weight e0
-      {
-        const int srow = wt & 127, h2 = (wt >> 7) * 2;
-        const bool live = srow < rows_used;
-        const int ln = live ? srow / p.T : 0, rb = ln * p.T;
-        const float c0 = h2 ? scls2 : scls0, c1 = h2 ? scls3 : scls1;
-        float m0 = c0, m1 = c1;
-        if (live) {
-          for (int n = 0; n < p.T; ++n) {
-            const float2 a = *reinterpret_cast<const float2*>(&sSc[(rb + n) * 4 + h2]);
-            const float2 b = *reinterpret_cast<const float2*>(&sSc[(128 + rb + n) * 4 + h2]);
-            m0 = fmaxf(m0, a.x + b.x);
-            m1 = fmaxf(m1, a.y + b.y);
-          }
-          const float2 a = *reinterpret_cast<const float2*>(&sSc[srow * 4 + h2]);
-          const float2 b = *reinterpret_cast<const float2*>(&sSc[(128 + srow) * 4 + h2]);
-          *reinterpret_cast<float2*>(&sP[srow * 4 + h2]) = make_float2(expf(a.x + b.x - m0), expf(a.y + b.y - m1));
-        }
-        worker_sync();
-        if (live && srow == rb) {
-          const float e0 = expf(c0 - m0), e1 = expf(c1 - m1);
-          float s0 = e0, s1 = e1;
-          for (int n = 0; n < p.T; ++n) {
-            const float2 e = *reinterpret_cast<const float2*>(&sP[(rb + n) * 4 + h2]);
-            s0 += e.x;
-            s1 += e.y;
-          }
-          *reinterpret_cast<float2*>(&sInv[ln * 4 + h2]) = make_float2(1.f / s0, 1.f / s1);
-          *reinterpret_cast<float2*>(&sP[1024 + ln * 4 + h2]) = make_float2(e0, e1);
-        }
-        worker_sync();
-      }
-      if (tr) LTR_DBG_STAMP(9);
-      // ---- pooling: z_h[c] = (e0 * cls[c] + sum_n e[n] x[n][c]) / sum.  Thread = (4 channels, 2 of the
-      //      4 heads, every second line): one 16-byte x read feeds 8 FMAs (a thread per channel was
-      //      latency-bound at 2 loads per 4 FMAs).  Up to three of the thread's lines run interleaved - 24 independent
-      //      accumulators - so the two loads of a token hide behind the FMAs of the other lines.
-      {
-        const int cq = wt & 63, lg = (wt >> 6) & 1, hp = wt >> 7;
-        const float4 cv = *reinterpret_cast<const float4*>(&sCls[cq * 4]);
-        for (int l0 = lg; l0 < p.lpt; l0 += 6) {
-          float za[3][4], zb[3][4];
-          int rb[3];
-          bool ok[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int ln = l0 + 2 * i;
-            ok[i] = ln < p.lpt && line0 + ln < p.R;
-            rb[i] = ok[i] ? ln * p.T : 0;
-            const float2 pc = ok[i] ? *reinterpret_cast<const float2*>(&sP[1024 + ln * 4 + 2 * hp]) : make_float2(0.f, 0.f);
-            za[i][0] = pc.x * cv.x; za[i][1] = pc.x * cv.y; za[i][2] = pc.x * cv.z; za[i][3] = pc.x * cv.w;
-            zb[i][0] = pc.y * cv.x; zb[i][1] = pc.y * cv.y; zb[i][2] = pc.y * cv.z; zb[i][3] = pc.y * cv.w;
-          }
-#pragma unroll 2
-          for (int n = 0; n < p.T; ++n) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const float4 xv = *reinterpret_cast<const float4*>(&xs[xs_index(rb[i] + n, cq * 4)]);
-              const float2 pr = *reinterpret_cast<const float2*>(&sP[(rb[i] + n) * 4 + 2 * hp]);
-              za[i][0] = fmaf(pr.x, xv.x, za[i][0]); za[i][1] = fmaf(pr.x, xv.y, za[i][1]);
-              za[i][2] = fmaf(pr.x, xv.z, za[i][2]); za[i][3] = fmaf(pr.x, xv.w, za[i][3]);
-              zb[i][0] = fmaf(pr.y, xv.x, zb[i][0]); zb[i][1] = fmaf(pr.y, xv.y, zb[i][1]);
-              zb[i][2] = fmaf(pr.y, xv.z, zb[i][2]); zb[i][3] = fmaf(pr.y, xv.w, zb[i][3]);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            if (!ok[i]) continue;
-            const int ln = l0 + 2 * i, gl = line0 + ln;
-            const float2 iv = *reinterpret_cast<const float2*>(&sInv[ln * 4 + 2 * hp]);
-            img_store4(p.z, gl, (2 * hp) * 256 + cq * 4, za[i][0] * iv.x, za[i][1] * iv.x, za[i][2] * iv.x, za[i][3] * iv.x);
-            img_store4(p.z, gl, (2 * hp + 1) * 256 + cq * 4, zb[i][0] * iv.y, zb[i][1] * iv.y, zb[i][2] * iv.y, zb[i][3] * iv.y);
-          }
-        }
-      }
-      if (tr) LTR_DBG_STAMP(10);
-      worker_sync();   // x tile and probabilities are dead: the next tile may overwrite them
-      ptx::fence_proxy_async_smem();   // this thread's generic accesses to the x tile before the TMA writes that follow
-      ptx::mbar_arrive(x_free);        // -> the MMA thread requests the next tile's descriptors
+      // softmax + pooling of THIS tile run inside the next tile's MMA phases (or after the loop for the last one)
+      prev_line0 = line0;
+      have_prev = true;
       if (tr) LTR_DBG_STAMP(11);
+    }
+    if (have_prev) {   // drain: the CTA's last tile
+      softmax_prev();
+      pool_prev(0, 1 << 30);
     }
   }
   ptx::tc_fence_before();

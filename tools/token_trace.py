@@ -17,10 +17,12 @@ lib.ltr_debug_trace_read(buf)
 lib.ltr_debug_trace_arm(0)
 v = [buf[i] for i in range(12)]
 a = [buf[i] for i in range(30, 39)]
-names = ["P0 start", "P0 done", "L3 acc", "ep3 done", "L4 acc", "ep4 done", "L5 acc", "ep5 done", "sync", "softmax done", "pool done", "tile end"]
-for i in range(1, 12):
-    print(f"{names[i]:14s} +{v[i]-v[i-1]:7d} cycles")
-print("tile total", v[11] - v[0])
+names = {1: "ep2 done", 2: "L3 acc", 3: "ep3 done", 4: "L4 acc (nb0)", 5: "ep4 done", 6: "L5 acc (nb0)", 7: "ep5 done", 11: "tile end"}
+prev = v[0]
+for i in (1, 2, 3, 4, 5, 6, 7, 11):
+    print(f"{names[i]:14s} +{v[i]-prev:7d} cycles")
+    prev = v[i]
+print("tile total", v[11] - v[0], " (softmax + pooling of a tile run inside the next tile's MMA phases)")
 print("L5 second n-block complete", buf[12] - v[6], "cycles after the first")
 
 an = ["start", "tmem alloc+sync", "kt start", "stage q,k", "stage v^T", "S mma done", "softmax+P stored", "PV mma done", "epilogue done"]
