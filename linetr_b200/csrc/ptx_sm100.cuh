@@ -368,6 +368,13 @@ __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint
   const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
+// the same with the two residuals from ONE packed fp32 operation (fma.rn.f32x2, sm_100): (a, b) - (hi_a, hi_b) is exact,
+// so the result is bit-identical; one instruction less per pair in the issue-bound epilogues
+__device__ __forceinline__ void split2_bf16_x2(float2 v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.y), "f"(v.x));
+  const float2 r = __ffma2_rn(make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u)), make_float2(-1.f, -1.f), v);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
+}
 __device__ __forceinline__ void split8_bf16(const float* v, uint4& hi, uint4& lo) {
   split2_bf16(v[0], v[1], hi.x, lo.x);
   split2_bf16(v[2], v[3], hi.y, lo.y);

@@ -234,8 +234,10 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
     auto act_store32 = [&](const float (&acc)[32], const float* bias, uint32_t t_hi, uint32_t t_lo) {
       uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2)
-        ptx::split2_bf16(fmaxf(acc[j] + bias[j], 0.f), fmaxf(acc[j + 1] + bias[j + 1], 0.f), hi[j >> 1], lo[j >> 1]);
+      for (int j = 0; j < 32; j += 2) {   // packed fp32 pairs (add.f32x2 / fma.f32x2): half the issue slots of the scalar form
+        const float2 v = __fadd2_rn(make_float2(acc[j], acc[j + 1]), *reinterpret_cast<const float2*>(bias + j));
+        ptx::split2_bf16_x2(make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)), hi[j >> 1], lo[j >> 1]);
+      }
       ptx::tmem_st16(lane_addr + t_hi, hi);
       ptx::tmem_st16(lane_addr + t_lo, lo);
     };
@@ -358,8 +360,10 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
           const float prv[4] = {pr.x, pr.y, pr.z, pr.w};
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            z[h][0] = fmaf(prv[h], xv.x, z[h][0]); z[h][1] = fmaf(prv[h], xv.y, z[h][1]);
-            z[h][2] = fmaf(prv[h], xv.z, z[h][2]); z[h][3] = fmaf(prv[h], xv.w, z[h][3]);
+            const float2 pp = make_float2(prv[h], prv[h]);
+            const float2 za = __ffma2_rn(pp, make_float2(xv.x, xv.y), make_float2(z[h][0], z[h][1]));
+            const float2 zb = __ffma2_rn(pp, make_float2(xv.z, xv.w), make_float2(z[h][2], z[h][3]));
+            z[h][0] = za.x; z[h][1] = za.y; z[h][2] = zb.x; z[h][3] = zb.y;
           }
         }
         const float4 iv = *reinterpret_cast<const float4*>(&sInv[ln * 4]);
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
       }
       // ---- epilogue L5: x = acc + b5 + desc -> fp32, in place in the x tile (where the TMA put desc);
       //      partial CLS scores over this thread's 128 columns (64 of each n-block, first n-block first)
-      float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
+      float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
 #pragma unroll 1
       for (int nb = 0; nb < 2; ++nb) {
         if (nb == 0) ptx::mbar_wait(&acc_bar[0], nacc0++ & 1);
@@ -456,26 +460,25 @@ __global__ void __launch_bounds__(320, 1) token_fused_kernel(TokenFusedArgs p, c
             const int n = c0 + j;
             float4* xp = reinterpret_cast<float4*>(&xs[xs_index(r_in, n)]);
             const float4 d = *xp;
-            float4 x;
-            x.x = acc[j] + sB5[n] + d.x;
-            x.y = acc[j + 1] + sB5[n + 1] + d.y;
-            x.z = acc[j + 2] + sB5[n + 2] + d.z;
-            x.w = acc[j + 3] + sB5[n + 3] + d.w;
-            *xp = x;
+            const float4 b = *reinterpret_cast<const float4*>(&sB5[n]);
+            // packed fp32 pairs: per head an (even, odd) column pair of partial scores, summed after the loop
+            const float2 xa = __fadd2_rn(__fadd2_rn(make_float2(acc[j], acc[j + 1]), make_float2(b.x, b.y)), make_float2(d.x, d.y));
+            const float2 xb = __fadd2_rn(__fadd2_rn(make_float2(acc[j + 2], acc[j + 3]), make_float2(b.z, b.w)), make_float2(d.z, d.w));
+            *xp = make_float4(xa.x, xa.y, xb.x, xb.y);
             const float4 u0 = *reinterpret_cast<const float4*>(&sU[n]);
             const float4 u1 = *reinterpret_cast<const float4*>(&sU[256 + n]);
             const float4 u2 = *reinterpret_cast<const float4*>(&sU[512 + n]);
             const float4 u3 = *reinterpret_cast<const float4*>(&sU[768 + n]);
-            sc0 = fmaf(x.x, u0.x, fmaf(x.y, u0.y, fmaf(x.z, u0.z, fmaf(x.w, u0.w, sc0))));
-            sc1 = fmaf(x.x, u1.x, fmaf(x.y, u1.y, fmaf(x.z, u1.z, fmaf(x.w, u1.w, sc1))));
-            sc2 = fmaf(x.x, u2.x, fmaf(x.y, u2.y, fmaf(x.z, u2.z, fmaf(x.w, u2.w, sc2))));
-            sc3 = fmaf(x.x, u3.x, fmaf(x.y, u3.y, fmaf(x.z, u3.z, fmaf(x.w, u3.w, sc3))));
+            s0 = __ffma2_rn(xa, make_float2(u0.x, u0.y), __ffma2_rn(xb, make_float2(u0.z, u0.w), s0));
+            s1 = __ffma2_rn(xa, make_float2(u1.x, u1.y), __ffma2_rn(xb, make_float2(u1.z, u1.w), s1));
+            s2 = __ffma2_rn(xa, make_float2(u2.x, u2.y), __ffma2_rn(xb, make_float2(u2.z, u2.w), s2));
+            s3 = __ffma2_rn(xa, make_float2(u3.x, u3.y), __ffma2_rn(xb, make_float2(u3.z, u3.w), s3));
           }
         }
       }
       dph ^= 1;
       ptx::tc_fence_before();
-      *reinterpret_cast<float4*>(&sSc[(half * 128 + r_in) * 4]) = make_float4(sc0, sc1, sc2, sc3);
+      *reinterpret_cast<float4*>(&sSc[(half * 128 + r_in) * 4]) = make_float4(s0.x + s0.y, s1.x + s1.y, s2.x + s2.y, s3.x + s3.y);
       if (tr) LTR_DBG_STAMP(7);
       worker_sync();
       if (tr) LTR_DBG_STAMP(8);
