@@ -901,15 +901,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
                 ptx::bulk_wait_read_all();            // the copies have read staging tile b: hand it back (the epilogue
                 ptx::mbar_arrive(&tile_free[b]);      // is filling the other tile meanwhile)
                 // publish what is in memory.  Waiting for THIS k-block's store here would make the store round trip
-                // (~1.2 k cycles, trace) the period of the whole epilogue: let one store stay in flight, except for
-                // the tile's last k-block (the next op needs it before this CTA produces anything else)
-                if (kbl == 3) ptx::bulk_wait_all();
-                else ptx::bulk_wait_but_one();
-                const uint32_t n = kbl == 3 ? unpub : unpub - 1;
-                if (n) {
-                  __threadfence_block();
-                  *seq_done = *seq_done + n;
-                  unpub -= n;
+                // (~4 k cycles until the write is complete, trace) the period of the whole epilogue: let one store stay
+                // in flight, except for the tile's last k-block (the next op needs it before this CTA produces anything
+                // else).  Nobody inside this launch reads what the LAST op writes: its stores only have to be done
+                // reading the staging tile (above) - the grid's completion makes them visible to the next kernel - so the
+                // CTA does not sit out a store round trip at the end of every launch.
+                if (o + 1 < c.n_ops || ct + cl_step < n_ctiles) {
+                  if (kbl == 3) ptx::bulk_wait_all();
+                  else ptx::bulk_wait_but_one();
+                  const uint32_t n = kbl == 3 ? unpub : unpub - 1;
+                  if (n) {
+                    __threadfence_block();
+                    *seq_done = *seq_done + n;
+                    unpub -= n;
+                  }
                 }
                 if (hs < 24) LTR_DBG_STAMP(16 + hs);   // trace: hand-over hs processed (published up to here)
               }
