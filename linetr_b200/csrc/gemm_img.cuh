@@ -707,6 +707,17 @@ __device__ __forceinline__ void mbar_wait_dl(uint64_t* bar, uint32_t parity, boo
 // Tiles with an image output and no fp32-row side inputs leave through the streamed epilogue (row norms included; fp32
 // rows C are written straight from registers); anything else takes the per-warp staged path.
 __device__ __forceinline__ bool chain2_streamed(const GemmImgArgs& p) { return p.O.hi && !p.R && !p.nadd; }
+// The output tiles of a streamed op ARE the A operand tiles of the next op of the chain (same rows, same layout): the
+// epilogue warps write every finished k-block ALSO into the ring slot of that A tile and arrive on its `full` barrier (one
+// arrival per warp; a TMA fill arrives with count 8, so every use of a slot is one phase whoever filled it), next to
+// the staging tile the store warp ships to global memory.  Through memory the next op's first MMAs waited ~4 k cycles
+// for the store to complete plus ~2 k for the load (clock64 trace, profiles/r2_chain_trace.md) at every op boundary.
+// (A shared -> shared bulk copy by the store warp does the same without the second set of stores, but moved 32 KB in
+// ~4 k cycles - it was slower than the round trip through L2.)
+// Only for ops with ONE n-block: their four output k-blocks map to ring uses at most 7 beyond the op's last one, so the
+// writers wait for a slot at most one mbarrier phase ahead (the parity wait cannot tell phases two apart); the first
+// n-block of a wider op would have to be handed over while the op's later n-blocks still cycle the ring.
+__device__ __forceinline__ bool chain2_direct(const GemmImgArgs& p) { return chain2_streamed(p) && p.n_blks == 1; }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_kernel(const __grid_constant__ GemmChainArgs c) {
   using Cfg = GemmPairCfg;
@@ -733,7 +744,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::SLOTS; ++s) {
-      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&full[s], 8);   // a TMA fill arrives with count 8; a direct hand-over = one arrival per epilogue warp
       ptx::mbar_init(&peer_full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
@@ -768,7 +779,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
         mbar_wait_dl(&empty[sl], phase_of(u) ^ 1, true);
         uint8_t* st = smem + sl * Cfg::SLOT;
         const size_t woff = ((size_t)kb * (p.W.N / 8) + (size_t)nb * (BN / 8) + (size_t)rank * 16) * 1024;
-        ptx::mbar_arrive_expect_tx(&full[sl], Cfg::SLOT);
+        ptx::mbar_expect_tx(&full[sl], Cfg::SLOT);
+        ptx::mbar_arrive_cnt(&full[sl], 8);
         ptx::bulk_g2s(st, reinterpret_cast<const uint8_t*>(p.W.hi) + woff, Cfg::W_HALF, &full[sl]);
         ptx::bulk_g2s(st + Cfg::W_HALF, reinterpret_cast<const uint8_t*>(p.W.lo) + woff, Cfg::W_HALF, &full[sl]);
       };
@@ -791,9 +803,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
           for (int nb = 0; nb < p.n_blks; ++nb)
             for (int kb = 0; kb < nk; ++kb, ++it) {
               if ((int)it >= pre) load_w(p, nb, kb, 2u * it);
-              if (o > 0 && nb == 0) {
-                // A k-block kb of this op = output k-block kb of the previous op (same m-tile, same CTA): wait until
-                // the epilogue has published it (bulk store completed / generic stores fenced)
+              // A k-block kb of this op = output k-block kb of the previous op (same m-tile, same CTA).  For the first
+              // n-block the store warp copies it from the staging tile straight into this ring slot (chain2_direct) -
+              // nothing to do here; later n-blocks re-read it from global memory, after the store has been published
+              const bool direct = o > 0 && chain2_direct(c.op[o - 1]);
+              if (direct && nb == 0) continue;
+              if (o > 0 && (nb == 0 || direct)) {
+                // wait until the epilogue has published it (bulk store completed / generic stores fenced)
                 const uint32_t need = seq_prev + (uint32_t)kb + 1;
                 if (*seq_done < need) {
                   const long long t0 = clock64();
@@ -809,7 +825,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
               mbar_wait_dl(&empty[sl], phase_of(u) ^ 1, true);
               uint8_t* st = smem + sl * Cfg::SLOT;
               const size_t aoff = ((size_t)mt * p.A.kblocks + p.a_kb0 + kb) * IMG_TILE_ELEMS;
-              ptx::mbar_arrive_expect_tx(&full[sl], Cfg::SLOT);
+              ptx::mbar_expect_tx(&full[sl], Cfg::SLOT);
+              ptx::mbar_arrive_cnt(&full[sl], 8);
               ptx::bulk_g2s(st, p.A.hi + aoff, Cfg::A_TILE, &full[sl]);
               ptx::bulk_g2s(st + Cfg::A_TILE, p.A.lo + aoff, Cfg::A_TILE, &full[sl]);
             }
@@ -951,11 +968,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
     auto sel4 = [](const float (&a)[4], int k) { return k == 0 ? a[0] : k == 1 ? a[1] : k == 2 ? a[2] : a[3]; };
     float bcur[4] = {0.f, 0.f, 0.f, 0.f}, bnxt[4] = {0.f, 0.f, 0.f, 0.f};
     if (cl0 < n_ctiles) col_vec(c.op[0].bias, 0, bcur);
+    uint32_t it_cnt = 0;                            // ring k-blocks of all ops so far (the producer's `it` at the end of the op)
     for (int ct = cl0; ct < n_ctiles; ct += cl_step) {
       const int mt = 2 * ct + (int)rank;
       for (int o = 0; o < c.n_ops; ++o) {
         const GemmImgArgs& p = c.op[o];
         const bool streamed = chain2_streamed(p);
+        it_cnt += (uint32_t)(p.n_blks * (p.W.K / 64));
+        // direct hand-over (chain2_direct): output k-block j of this op = A k-block j of the next op's first n-block,
+        // ring use 2 (it_cnt + j) + 1
+        const int nk_next = (o + 1 < c.n_ops && chain2_direct(p)) ? c.op[o + 1].W.K / 64 : 0;
         for (int nb = 0; nb < p.n_blks; ++nb, ++tl) {
           const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
           {   // next tile of this CTA (this op's next n-block, the next op, the next cluster tile)
@@ -1126,9 +1148,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
                 *reinterpret_cast<uint4*>(tile + off) = h[cc];
                 *reinterpret_cast<uint4*>(tile + 16384 + off) = l[cc];
               }
-              ptx::fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&tile_ready[sb]);
+              if (kbl < nk_next) {   // the same 64 B per plane also into the next op's A slot (n_blks == 1: nb == 0)
+                const uint32_t uc = 2u * (it_cnt + (uint32_t)kbl) + 1u;
+                const int slc = slot_of(uc);
+                uint8_t* aslot = smem + slc * Cfg::SLOT;
+                mbar_wait_dl(&empty[slc], phase_of(uc) ^ 1, true);   // the MMAs that read the slot's previous tile are complete
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                  const uint32_t off = ptx::sw128_offset(r_in, (c0 & 63) + cc * 8);
+                  *reinterpret_cast<uint4*>(aslot + off) = h[cc];
+                  *reinterpret_cast<uint4*>(aslot + Cfg::A_TILE + off) = l[cc];
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  ptx::mbar_arrive(&tile_ready[sb]);
+                  ptx::mbar_arrive(&full[slc]);
+                }
+              } else {
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tile_ready[sb]);
+              }
               if (tl == 2 && kbl == 0 && lane == 0) LTR_DBG_STAMP(90 + warp - 2);   // trace: per-warp first hand-over of the third tile
             }
           } else {

@@ -46,6 +46,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// transaction bytes announced without an arrival / an arrival that counts `cnt` times
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t cnt) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt) : "memory");
+}
 // non-blocking phase test (no hardware suspend: the caller spins)
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -82,6 +89,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // shared::cta -> global bulk copy (TMA store, 1-D), tracked by the issuing thread's bulk async-groups
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+// shared -> shared bulk copy inside the cluster (here: inside the own CTA): destination and mbarrier are
+// shared::cluster addresses (mapa_shared), the copy completes `bytes` of transaction count on the mbarrier
+__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster_addr, const void* smem_src, uint32_t bytes, uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+               "r"(smem_u32(smem_src)), "r"(bytes), "r"(mbar_cluster_addr)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

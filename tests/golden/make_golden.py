@@ -155,5 +155,27 @@ def main():
           {k: v.get("n_matches") for k, v in meta["cases"].items() if "n_matches" in v})
 
 
+def main_full():
+    """Full-size images of BASELINE.json's cfg[2] / cfg[3] shapes through the unmodified reference with the shipped
+    checkpoint: 256 lines x 32 tokens, and 512 lines x 64 tokens with ragged real-token counts.  Separate fixture
+    file (outputs only, ~0.7 MB): `reference_outputs_full.npz|json`."""
+    out, meta = {}, {"torch": torch.__version__, "numpy": np.__version__, "cases": {}}
+    sdr = {k: v.numpy() for k, v in torch.load(REAL_WEIGHTS).items()}
+    mr = ref_model(sdr, 1)
+    for name, c in {"real_enc_L256_T32": dict(seed=71, L=256, T=32, ntok=None),
+                    "real_enc_L512_T64_ragged": dict(seed=72, L=512, T=64, ntok=(3, 64))}.items():
+        d = syn.make_image_inputs(c["seed"], c["L"], c["T"], c["ntok"])
+        out[name] = run_forward(mr, d)
+        meta["cases"][name] = {**c, "weights": "shipped", "checksum": checksum(d)}
+        print(name, out[name].shape)
+    np.savez_compressed(os.path.join(HERE, "reference_outputs_full.npz"), **out)
+    with open(os.path.join(HERE, "reference_outputs_full.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "--full-only" in sys.argv:
+        main_full()
+    else:
+        main()
+        main_full()

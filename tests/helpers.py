@@ -18,6 +18,19 @@ def golden():
     return _cache["npz"], _cache["meta"]
 
 
+def golden_full():
+    """Full-size images (256 x 32, ragged 512 x 64) through the reference with the shipped checkpoint
+    (tests/golden/make_golden.py::main_full)."""
+    if "npz_full" not in _cache:
+        _cache["npz_full"] = dict(np.load(os.path.join(GOLDEN_DIR, "reference_outputs_full.npz")))
+        with open(os.path.join(GOLDEN_DIR, "reference_outputs_full.json")) as f:
+            _cache["meta_full"] = json.load(f)
+    return _cache["npz_full"], _cache["meta_full"]
+
+
+FULL_CASES = ["real_enc_L256_T32", "real_enc_L512_T64_ragged"]
+
+
 def checksum(d):
     return {k: float(np.asarray(v, dtype=np.float64).sum()) for k, v in sorted(d.items())}
 

@@ -125,6 +125,21 @@ def test_forward_vs_reference_golden_and_oracle(name):
     assert np.abs(np.linalg.norm(got, axis=1) - 1).max() < 1e-5
 
 
+@pytest.mark.parametrize("name", H.FULL_CASES)
+def test_forward_full_size_vs_reference_golden(name):
+    """Full-size images (256 lines x 32 tokens; 512 lines x 64 tokens, ragged token counts) with the shipped
+    checkpoint against outputs of the unmodified reference committed under tests/golden/."""
+    npz, meta = H.golden_full()
+    case = meta["cases"][name]
+    model, _ = model_for(case["weights"])
+    data = H.case_inputs(case)
+    H.assert_checksum(data, case["checksum"])
+    got = fwd(model, data)
+    assert got.shape == npz[name].shape
+    assert np.abs(got - npz[name]).max() < DESC_TOL_TIGHT
+    assert np.abs(np.linalg.norm(got, axis=1) - 1).max() < 1e-5
+
+
 def test_forward_batched_and_inplace_contract():
     npz, meta = H.golden()
     case = meta["cases"]["enc_B2_L12_T21"]

@@ -20,6 +20,21 @@ def test_forward_matches_reference(name):
     assert np.abs(got - npz[name]).max() < TOL
 
 
+@pytest.mark.parametrize("name", H.FULL_CASES)
+def test_forward_matches_reference_full_size(name):
+    """cfg[2] / cfg[3]-sized images with the shipped checkpoint: the oracle against the committed reference output."""
+    sd = H.load_shipped_weights()
+    if sd is None:
+        pytest.skip("shipped checkpoint not available")
+    npz, meta = H.golden_full()
+    case = meta["cases"][name]
+    data = H.case_inputs(case)
+    H.assert_checksum(data, case["checksum"])
+    got = orc.line_transformer_forward(sd, data)
+    assert got.shape == npz[name].shape
+    assert np.abs(got - npz[name]).max() < TOL
+
+
 def test_forward_batched():
     npz, meta = H.golden()
     case = meta["cases"]["enc_B2_L12_T21"]

@@ -20,6 +20,6 @@ ncu --set full --clock-control none --cache-control none -k "$KREG" -s 21 -c 21 
     python bench.py --profile-only --steps 1 --warmup 1 "$@" > $OUT/${TAG}_ncu2.log 2>&1; echo "ncu live rc=$?"
 ncu -i $TMP/full_live.ncu-rep --page raw --csv > $OUT/${TAG}_full_live_raw.csv 2>/dev/null
 # token kernel, V projection, line chain? no: first chain (fc .. qkv0), attention, layer chain of one step, with SASS/source
-ncu --set full --clock-control none --import-source on -k "regex:token_fused|gemm_chain|sig_attention|match_tc" -s 11 -c 4 -f -o $OUT/${TAG}_src4 \
-    python bench.py --profile-only --steps 1 --warmup 1 "$@" > $OUT/${TAG}_ncu3.log 2>&1; echo "ncu src rc=$?"
+# (source-level capture dropped from the default run: the binary report alone is ~10 MB)
+
 ls -la $OUT | tail -10; du -sm $OUT
