@@ -366,7 +366,7 @@ def main():
     # tail kernel - its last block stores the counts into every rank's symmetric buffer over NVLink (multimem.st
     # / peer stores), no NCCL kernel competes with the persistent CTAs for an SM slot.  LTR_BENCH_GATHER=nccl:
     # ncclAllGather on NCCL's stream (the round-1 path).
-    gather_mode = os.environ.get("LTR_BENCH_GATHER", "p2p") if world > 1 else "none"
+    gather_mode = os.environ.get("LTR_BENCH_GATHER", "p2p") if world > 1 else "none"   # "off": diagnosis, no exchange at all
     peer = None
     if gather_mode == "p2p":
         try:
@@ -378,8 +378,10 @@ def main():
     pending = []   # all-gathers in flight: the gather of step i overlaps the kernels of step i+1
     gathered = {}
 
-    def drain():
-        while pending:
+    KEEP = int(os.environ.get("LTR_BENCH_KEEP", "0"))   # diagnosis: gathers left in flight across a step boundary
+
+    def drain(keep=0):
+        while len(pending) > keep:
             h = pending.pop(0)[1]
             gathered["last"] = h.result() if peer is not None else h.wait()
 
@@ -394,12 +396,12 @@ def main():
     def step_resident():
         if peer is not None:
             m0, cnt = run_resident(peer.publish())
-            drain()                                      # counts of step i-1 (its D2H copy ran under step i's kernels)
+            drain(KEEP)                                  # counts of step i-1 (its D2H copy ran under step i's kernels)
             pending.append((None, peer.collect_async())) # copy-engine D2H of this step's slot behind this step's kernels
             return m0, cnt
         m0, cnt = run_resident()
-        if world > 1:
-            drain()
+        if world > 1 and gather_mode != "off":
+            drain(KEEP)
             pending.append(gather_counts(cnt, P * world, async_op=True))
         return m0, cnt
 
