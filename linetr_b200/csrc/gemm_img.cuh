@@ -89,6 +89,25 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x < 0.f ? g : x - g;
 }
 
+// two values at once with packed fp32 arithmetic (mul/fma.f32x2): the same operations in the same order as gelu_erf,
+// bit-identical results, ~21 instead of ~34 issue slots per pair (the 256 -> 1024 FFN tiles are epilogue-bound)
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 u = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), u, make_float2(1.f, 1.f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  float2 pl = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  pl = __ffma2_rn(pl, t, make_float2(1.421413741f, 1.421413741f));
+  pl = __ffma2_rn(pl, t, make_float2(-0.284496736f, -0.284496736f));
+  pl = __ffma2_rn(pl, t, make_float2(0.254829592f, 0.254829592f));
+  pl = __fmul2_rn(pl, t);
+  const float2 arg = __fmul2_rn(__fmul2_rn(u, u), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e = make_float2(ptx::ex2_approx(arg.x), ptx::ex2_approx(arg.y));
+  const float2 g = __fmul2_rn(__fmul2_rn(__fmul2_rn(make_float2(0.5f, 0.5f), x), pl), e);   // 0.5 x erfc(|x| / sqrt 2)
+  return make_float2(x.x < 0.f ? g.x : x.x - g.x, x.y < 0.f ? g.y : x.y - g.y);
+}
+
 // ---------------------------------------------------------------- epilogue building blocks
 // One epilogue warp owns 32 accumulator rows (row0 .. row0+31, lane = row) and works on 32-column
 // chunks `acc[32]` starting at global column `nbase`.  Global traffic goes through the warp's 4 KB
@@ -325,7 +344,10 @@ __device__ __forceinline__ void epi_plain_tile(const GemmImgArgs& p, uint32_t tm
       for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
     } else if (p.act == ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+      for (int j = 0; j < 32; j += 2) {
+        const float2 g = gelu_erf2(make_float2(acc[j], acc[j + 1]));
+        acc[j] = g.x; acc[j + 1] = g.y;
+      }
     }
     if (p.R) epi_add_rows_f32(p.R, p.ldr, row0, nbase, p.M, lane, stg, acc);
     if (p.Rimg.hi) epi_add_rows_img(p.Rimg, p.r_kb0, mt, nbase, q, row0, p.M, lane, stgb, acc);
@@ -1029,7 +1051,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
           auto add_bias = [&](float (&acc)[32], int kbl) {
             const float bk = sel4(bcur, kbl);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] += __shfl_sync(0xffffffffu, bk, j);
+            for (int j = 0; j < 32; j += 2) {   // packed fp32 pair add (add.f32x2): bit-identical, half the issue slots
+              const float2 v = __fadd2_rn(make_float2(acc[j], acc[j + 1]),
+                                          make_float2(__shfl_sync(0xffffffffu, bk, j), __shfl_sync(0xffffffffu, bk, j + 1)));
+              acc[j] = v.x; acc[j + 1] = v.y;
+            }
           };
           if (streamed && res_hi) img_load(res_hi, res_lo, res_t0);
           mbar_wait_dl(&acc_full[buf], aph, true);
@@ -1106,7 +1132,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1) gemm_chain2_
                   for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
                 } else if (act == ACT_GELU) {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
+                  for (int j = 0; j < 32; j += 2) {
+                    const float2 g = gelu_erf2(make_float2(acc[j], acc[j + 1]));
+                    acc[j] = g.x; acc[j + 1] = g.y;
+                  }
                 }
                 if (res_hi) {
                   img_add(acc);

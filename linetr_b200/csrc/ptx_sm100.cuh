@@ -390,10 +390,10 @@ __device__ __forceinline__ void split2_bf16_x2(float2 v, uint32_t& hi, uint32_t&
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
 }
 __device__ __forceinline__ void split8_bf16(const float* v, uint4& hi, uint4& lo) {
-  split2_bf16(v[0], v[1], hi.x, lo.x);
-  split2_bf16(v[2], v[3], hi.y, lo.y);
-  split2_bf16(v[4], v[5], hi.z, lo.z);
-  split2_bf16(v[6], v[7], hi.w, lo.w);
+  split2_bf16_x2(make_float2(v[0], v[1]), hi.x, lo.x);
+  split2_bf16_x2(make_float2(v[2], v[3]), hi.y, lo.y);
+  split2_bf16_x2(make_float2(v[4], v[5]), hi.z, lo.z);
+  split2_bf16_x2(make_float2(v[6], v[7]), hi.w, lo.w);
 }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
