@@ -1,3 +1,4 @@
+# Run on the GPU box (gpurun): everything the round-end record needs - tests, bench of all workloads, ncu summaries, launch list, latency, traces
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
 LTR_CHAIN_MIN_TILES=1 timeout 600 python -m pytest tests -m gpu -q -x -k "forward or varlen or full_size or cfg3 or pair or plumbing or shipped or ffn_width" 2>&1 | tail -2
 bash tools/gpu_profile.sh r2g 2>&1 | grep -E "rc=" 

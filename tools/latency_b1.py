@@ -62,6 +62,31 @@ for mode in ("eager", "cuda_graph"):
     ba, bb = LineBatch.from_images([a]).to(dev), LineBatch.from_images([b]).to(dev)
     if mode == "eager":
         out["engine_match_pairs_1_pair"] = timeit(lambda: eng.match_pairs(ba, bb, 0.8).counts)
+# ---- the same pair starting where `Matching` starts the plugin: SuperPoint's dense maps already on the device + detected key
+#      lines (host objects) -> GPU tokeniser (LineTransformer.preprocess -> ltr_tokenize) -> forward x2 -> matcher calls
+try:
+    from tests.test_tokenizer import fake_lines, fake_superpoint
+    m = LineTransformer({"mode": "test"})
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    m = m.eval().to(dev)
+    sp = [{k: v.to(dev) for k, v in fake_superpoint(s).items()} for s in (7, 8)]
+    kl = [fake_lines(7, 120), fake_lines(8, 120)]
+
+    def pair_from_maps():
+        p0 = m.preprocess(kl[0], (1, 1, 480, 640), sp[0], None)
+        p1 = m.preprocess(kl[1], (1, 1, 480, 640), sp[1], None)
+        d0 = m(p0)["line_desc"].cpu().numpy()
+        d1 = m(p1)["line_desc"].cpu().numpy()
+        dist = get_dist_matrix(d0, d1)[0]
+        dk = m.subline2keyline(dist, p0["mat_klines2sublines"][0], p1["mat_klines2sublines"][0])
+        return nn_matcher_distmat(dk, 0.8, True), int(p0["sublines"].shape[1]), int(p1["sublines"].shape[1])
+
+    _, s0, s1 = pair_from_maps()
+    out["pair_from_superpoint_maps_on_device"] = {**timeit(lambda: pair_from_maps(), n=60, warm=10),
+                                                  "sublines": [s0, s1], "note": "2 x (host line filtering + GPU tokeniser) + "
+                                                  "2 x forward + get_dist_matrix + subline2keyline + nn_matcher_distmat"}
+except Exception as e:   # the tool must not fail on the optional leg
+    out["pair_from_superpoint_maps_on_device"] = {"error": f"{type(e).__name__}: {e}"}
 leg = run_cpu_leg("cfg1", 8, 10, 3)
 out["cpu_port_8_threads"] = {"ms_per_pair_median": 1e3 * leg["s_per_pair_median"]}
 leg = run_cpu_leg("cfg1", 1, 10, 3)
