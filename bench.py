@@ -396,12 +396,19 @@ def main():
     def step_resident():
         if peer is not None:
             m0, cnt = run_resident(peer.publish())
-            drain(KEEP)                                  # counts of step i-1 (its D2H copy ran under step i's kernels)
+            # counts of step i-2: one exchange stays in flight across the step boundary.  A host that waits for the
+            # previous step's counts (and the peers' flags) before it enqueues the next step lets the launch queue run dry
+            # whenever the ranks drift into ping-pong - the same box measured 0.99 and 1.41 ms per step that way.  With
+            # LTR_GATHER_SLOTS = 8 a peer can only overwrite a slot 8 steps later, when this rank has long read it.
+            drain(max(KEEP, 1))
             pending.append((None, peer.collect_async())) # copy-engine D2H of this step's slot behind this step's kernels
             return m0, cnt
         m0, cnt = run_resident()
         if world > 1 and gather_mode != "off":
-            drain(KEEP)
+            # NCCL path: one all-gather stays in flight across the step boundary - its kernel has to find an SM between
+            # persistent CTAs that follow each other without a gap (PDL), and a host that waits for it every step lets
+            # the launch queue run dry (measured 1.41 ms per step against 1.05 ms)
+            drain(max(KEEP, 1))
             pending.append(gather_counts(cnt, P * world, async_op=True))
         return m0, cnt
 

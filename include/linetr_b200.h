@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define LTR_ABI_VERSION 2
+#define LTR_ABI_VERSION 3
 
 #define LTR_OK 0
 #define LTR_E_INVALID (-1)   /* bad argument / missing checkpoint tensor / shape mismatch */
@@ -170,7 +170,7 @@ typedef struct {
  * epoch the same way.  No NCCL kernel, no extra launch on the producing side; ltr_gather_wait (one tiny
  * block) waits for the `world` flags of a slot and copies the gathered counts out.  A rank may run at most
  * LTR_GATHER_SLOTS - 2 steps ahead of its own ltr_gather_wait calls. */
-#define LTR_GATHER_SLOTS 4
+#define LTR_GATHER_SLOTS 8
 typedef struct {
   void* mc_base;               /* multicast address of the symmetric buffer or NULL */
   void* const* peer_bases;     /* device array [world]: address of the buffer on every rank (used if !mc_base) */

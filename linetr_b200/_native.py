@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
 )
 # include/linetr_b200_debug.h (micro-benchmark / tracing hooks; not part of the drop-in boundary)
 DEBUG_SYMBOLS = ("ltr_gemm_bench", "ltr_gemm_trace", "ltr_debug_trace_arm", "ltr_debug_trace_read")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class LtrError(RuntimeError):
@@ -67,7 +67,7 @@ class LtrMatchInput(C.Structure):
                 ("tiles_row0_0", C.c_int32), ("tiles_row0_1", C.c_int32)]
 
 
-GATHER_SLOTS = 4
+GATHER_SLOTS = 8
 
 
 class LtrPeerGather(C.Structure):

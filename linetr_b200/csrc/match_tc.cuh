@@ -381,7 +381,7 @@ struct MatchTailArgs {
   int rank, world, gslot, epoch, n_pairs;
 };
 
-constexpr int GATHER_SLOTS = 4;
+constexpr int GATHER_SLOTS = 8;   // = LTR_GATHER_SLOTS
 __device__ __forceinline__ void multimem_st_u32(int* mc_addr, int v) {
   asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
 }

@@ -36,7 +36,7 @@ def test_header_symbols_exported():
     assert declared_dbg == set(N.DEBUG_SYMBOLS)
     for s in declared_dbg:
         assert hasattr(lib, s), f"{s} not exported"
-    assert N.load().ltr_abi_version() == N.ABI_VERSION == 2
+    assert N.load().ltr_abi_version() == N.ABI_VERSION == 3
 
 
 def test_state_dict_contract():

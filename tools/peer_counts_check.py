@@ -19,7 +19,7 @@ P, n0, n1 = 6, 200, 180
 ok = True
 for multicast in (True, False):
     pc = PeerCounts(P, multicast=multicast)
-    for step in range(7):     # > GATHER_SLOTS: slots and epochs wrap
+    for step in range(19):    # > 2 * GATHER_SLOTS: slots and epochs wrap
         thr = 0.3 + 0.1 * ((step + rank) % 5)     # different counts per rank and step
         pairs = [syn.make_descriptor_pair(1000 * rank + 10 * step + i, n0, n1)[:2] for i in range(P)]
         d0 = torch.from_numpy(np.concatenate([a.T for a, _ in pairs], 0).copy()).to(dev)
