@@ -678,16 +678,17 @@ __global__ void __launch_bounds__(320, 1) gemm_chain_kernel(const __grid_constan
 // Epilogue and op-to-op dependencies.  The trace of the first version (profiles/r2_chain_trace.md) showed the
 // MMA loop at the tensor peak but only 45 % of the launch inside it: at every op boundary the next op waited
 // for the WHOLE epilogue of the previous op's last tile (8-12 k cycles through per-warp staging + LDS + STG)
-// plus a fence and a TMA round trip.  Now image-only tiles are drained in k-block order: all 8 epilogue warps
-// work on the same 64-column k-block, write its hi / lo planes into one 32 KB staging tile in the image's own
-// swizzled layout and a dedicated STORE WARP (warp 10) stores them with two 16 KB bulk copies (TMA store);
-// epilogue and store warp hand the staging tile back and forth through two mbarriers (tile_ready: 8 warp
-// arrivals, tile_free: the bulk copies have read the tile), so no epilogue warp ever waits for a global
-// store to complete.  The store warp also publishes every finished output k-block in the shared sequence
+// plus a fence and a TMA round trip.  Now tiles with an image output are drained in k-block order (row norms
+// included: their statistics passes read the accumulator from TMEM, the biased values are written back with
+// tcgen05.st): all 8 epilogue warps work on the same 64-column k-block, write its hi / lo planes into one of two
+// 32 KB staging tiles in the image's own swizzled layout and a dedicated STORE WARP (warp 10) stores them with two
+// 16 KB bulk copies (TMA store); epilogue and store warp hand a staging tile back and forth through two mbarriers
+// (tile_ready: 8 warp arrivals, tile_free: the bulk copies have read the tile), so no epilogue warp ever waits for a
+// global store to complete.  The store warp also publishes every finished output k-block in the shared sequence
 // counter `seq_done`; the producer of the NEXT op loads A k-block j as soon as output k-block j of the previous
-// op is in memory - the next op's MMAs start while the previous tile is still being drained.  Tiles with fp32
-// row outputs / residuals or the row-norm epilogue keep the per-warp staging path (one hand-over per tile, four
-// k-blocks published at once).
+// op is in memory - the next op's MMAs start while the previous tile is still being drained - and ops with a single
+// n-block skip memory altogether (chain2_direct).  Only tiles with fp32-row side inputs keep the per-warp staging
+// path (one hand-over per tile, four k-blocks published at once); the encoder no longer produces any.
 struct GemmPairCfg {
   static constexpr int BN = 256;
   static constexpr int A_TILE = 16384;

@@ -59,7 +59,7 @@ struct TokenFusedArgs {
 };
 
 struct TokenFusedSmem {
-  static constexpr int ACT = 128 * 1024;   // activation region: h64/h128/h256 images, then x fp32
+  static constexpr int ACT = 128 * 1024;   // the descriptor / x tile (fp32); the activations live in tensor memory
   static constexpr int SLOT = 32 * 1024;   // one W tile [128 n x 64 k] hi + lo
   static constexpr int NSLOT = 2;
   static constexpr int OFF_RING = ACT;
@@ -77,7 +77,7 @@ struct TokenFusedSmem {
   static constexpr int TOTAL = OFF_BAR + 128 + 1024;       // + alignment slack
 };
 
-// x tile in the activation region: 8 column blocks of [128 rows x 32 fp32 (128 B)], each row's eight
+// x tile: 8 column blocks of [128 rows x 32 fp32 (128 B)], each row's eight
 // 16-byte chunks XOR-swizzled by row & 7 - the layout a SWIZZLE_128B tensor-map box load produces.
 // Conflict-free both for a thread per row (L5 epilogue) and for a thread per channel quad (pooling).
 __device__ __forceinline__ int xs_index(int row, int col) {
