@@ -39,6 +39,18 @@ def test_header_symbols_exported():
     assert N.load().ltr_abi_version() == N.ABI_VERSION == 3
 
 
+def test_header_constants_match_binding_and_kernels():
+    """The constants the C header, the ctypes binding and the kernels each spell out must agree (the exchange buffer of
+    the multi-GPU count publication is sized and indexed by LTR_GATHER_SLOTS on all three sides)."""
+    hdr = open(os.path.join(ROOT, "include", "linetr_b200.h")).read()
+    slots = int(re.search(r"#define\s+LTR_GATHER_SLOTS\s+(\d+)", hdr).group(1))
+    abi = int(re.search(r"#define\s+LTR_ABI_VERSION\s+(\d+)", hdr).group(1))
+    cu = open(os.path.join(ROOT, "linetr_b200", "csrc", "match_tc.cuh")).read()
+    assert slots == N.GATHER_SLOTS == int(re.search(r"constexpr int GATHER_SLOTS = (\d+);", cu).group(1))
+    assert abi == N.ABI_VERSION
+    assert slots >= 6   # one exchange may stay in flight across a step boundary (DESIGN.md section 6)
+
+
 def test_state_dict_contract():
     m = _model()
     spec = syn.state_dict_spec(1)
