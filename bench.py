@@ -19,6 +19,10 @@ K steps with a CUDA-event pair around every launch on the launching stream; sepa
 events do not serialise the kernels of the timed pass), `cpu_baseline` (oracle port on the host
 cores: median of >= 10 single-pair calls after 3 warm-ups, in a subprocess with the BLAS/OpenMP
 thread count pinned; one leg per thread setting, the best one is the baseline).
+
+Multi-GPU (torchrun): the per-pair match counts of all ranks reach every rank each step - by default stored by the matcher's
+tail kernel into every rank's symmetric buffer over NVLink (`LTR_BENCH_GATHER=p2p`), or `LTR_BENCH_GATHER=nccl` (all-gather);
+`off` and `LTR_BENCH_KEEP=n` (exchanges left in flight across a step boundary, default 1) exist for diagnosis.
 """
 import argparse
 import json
