@@ -2,7 +2,7 @@
 DRAM bytes, DRAM / L2 / tensor-pipe utilisation, occupancy, registers, shared memory; per kernel class the
 average DRAM traffic per launch (the `roofline.traffic` figure bench.py reads from profiles/r2_ncu_summary.json).
 
-    python tools/ncu_summary.py --out profiles/r2_ncu_summary.json flushed=gpurun_out/x_full_flush.ncu-rep live=gpurun_out/x_full_live.ncu-rep
+    python tools/ncu_summary.py --out profiles/r2_ncu_summary.json flushed=profiles/r2_ncu_full_flushed_raw.csv live=profiles/r2_ncu_full_live_raw.csv
 """
 import argparse
 import csv
